@@ -1,0 +1,154 @@
+/* lm_bev.h -- C-ABI of the B200-native BEV rasteriser (liblm_bev.so).
+ *
+ * What this boundary replaces.  The reference has NO FFI and no in-tree rasteriser: its
+ * BEV images come from an external tool (reference README.md:171-172) and enter the repo
+ * as files read by PIL (reference baseline/datasets/laserlane_proposals.py:85-98) and by
+ * the inverse map (reference baseline/utils/coor_img2pc.py:185-193).  The entry points
+ * below are what a ctypes/cffi stub inside the reference would bind to produce those
+ * files -- or the in-memory sample['proj'] tensor -- on a B200.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every *_dev pointer is DEVICE memory owned by the caller (PyTorch allocates and
+ *     frees it).  The library never allocates device memory and never synchronises the
+ *     device: it only enqueues kernels / memsets on the stream passed in
+ *     (a cudaStream_t carried as void*; NULL = legacy default stream).
+ *   - return value: 0 = OK; <0 = argument error detected before any launch (LM_ERR_*);
+ *     >0 = the cudaError_t of a failed launch.  lm_bev_last_error() gives the message
+ *     for the calling thread.  Re-entrant: no global mutable state besides that
+ *     thread-local message.
+ *   - device-side conditions that cannot be known before launch (workspace chunk pool
+ *     exhausted, per-cell count above the u32-sum limit) are reported in lm_bev_stats.error,
+ *     which lives at the start of the workspace.
+ */
+#ifndef LM_BEV_H
+#define LM_BEV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_BEV_ABI_VERSION 1
+
+/* u8 image channels.  Index 1 of a 3-channel cropped_tiff must be an elevation channel:
+ * reference baseline/utils/coor_img2pc.py:150 reads img[row, col, 1] as height. */
+enum {
+    LM_CH_MAX_I   = 0,  /* max quantised intensity                                     */
+    LM_CH_MEAN_I  = 1,  /* (sum_i + count/2) / count                                   */
+    LM_CH_MIN_Z   = 2,  /* min quantised height                                        */
+    LM_CH_MAX_Z   = 3,  /* max quantised height                                        */
+    LM_CH_MEAN_Z  = 4,  /* (sum_z + count/2) / count                                   */
+    LM_CH_DENSITY = 5,  /* min(count, 255): >= 1 in every occupied cell, so an occupied */
+                        /* pixel is never all-zero (coor_img2pc.py:78,106 empty rule)  */
+    LM_CH__COUNT  = 6
+};
+
+/* raw u32 accumulator planes, [LM_ACC_PLANES][height][width]; used to merge strip halos */
+enum {
+    LM_ACC_COUNT = 0, LM_ACC_SUM_I = 1, LM_ACC_SUM_Z = 2,
+    LM_ACC_MAX_I = 3, LM_ACC_MIN_Z = 4 /* 0xFFFFFFFF where count==0 */, LM_ACC_MAX_Z = 5,
+    LM_ACC_PLANES = 6
+};
+
+enum {
+    LM_ALGO_BINNED = 0, /* product path: bin -> index -> per-tile shared-memory reduce  */
+    LM_ALGO_DIRECT = 1  /* global-atomic accumulate + finalize; cross-check path        */
+};
+
+enum {
+    LM_OK = 0,
+    LM_ERR_INVALID = -1,     /* NULL / out-of-range argument                            */
+    LM_ERR_WORKSPACE = -2,   /* workspace too small or misaligned                       */
+    LM_ERR_UNSUPPORTED = -3  /* raster too large for one call (shard it by row window)  */
+};
+
+/* lm_bev_stats.error bits */
+enum {
+    LM_DEV_ERR_POOL = 1,      /* chunk pool exhausted (cannot happen with the size      */
+                              /* lm_bev_workspace_bytes returns)                        */
+    LM_DEV_ERR_CELL_OVERFLOW = 2 /* a cell received >= 2^24 points: u32 sums may wrap   */
+};
+
+/* Geometry and channel list.  Field names follow the keys of the sidecar
+ * cropped_tiff_param/<stem>.txt (reference baseline/utils/io_utils.py:125-150):
+ *   row = floor((x - bev_img_offset[0]) / img_reso[0])   (inverse of coor_img2pc.py:136-139)
+ *   col = floor((y - bev_img_offset[1]) / img_reso[1])
+ *   zq  = clamp(rint((z - local_min_ele) / ele_reso), 0, 255)   (inverse of :150)
+ *   iq  = (clamp(I, inten_min, inten_max) - inten_min) * 255 / (inten_max - inten_min)
+ *         (clip range: reference baseline/datasets/laserlane_proposals.py:626-628)
+ * all float steps are single IEEE binary32 operations; a point is kept iff
+ * row0 <= row < row0+height and col0 <= col < col0+width (never clamped), and is stored
+ * at (row-row0, col-col0).  |row0|+height and |col0|+width must stay below 2^24.       */
+typedef struct lm_bev_params {
+    int32_t height, width;        /* window size in cells                               */
+    int32_t row0, col0;           /* window origin in the global grid                   */
+    float   bev_img_offset[2];
+    float   img_reso[2];
+    float   local_min_ele;
+    float   ele_reso;
+    int32_t inten_min, inten_max; /* 0 <= inten_min < inten_max <= 65535                */
+    int32_t n_channels;           /* 1..4 u8 channels                                   */
+    int32_t channels[4];          /* LM_CH_*                                            */
+} lm_bev_params;
+
+/* Output buffers (device).  Any pointer may be NULL = not wanted, but at least one must
+ * be set.  Every cell of every requested buffer is written exactly once per call.      */
+typedef struct lm_bev_outputs {
+    uint8_t  *image_dev;    /* [height][width][n_channels] u8 (the PNG pixel layout)    */
+    uint16_t *count16_dev;  /* [height][width] u16 = min(count, 65535)                  */
+    float    *proj_dev;     /* [n_channels][height][width] f32 = u8/255: the loader's   */
+                            /* to_tensor(...).float() (laserlane_proposals.py:88-89)    */
+    uint32_t *acc_dev;      /* [LM_ACC_PLANES][height][width] raw accumulators          */
+    int32_t   acc_band;     /* acc_dev rows written: <=0 all rows; else only tiles that */
+                            /* intersect rows [0,band) or [height-band,height)          */
+    int32_t   reserved;
+} lm_bev_outputs;
+
+/* First bytes of the workspace after a call (read it back with a D2H copy if wanted). */
+typedef struct lm_bev_stats {
+    uint32_t error;         /* LM_DEV_ERR_* bits                                        */
+    uint32_t n_chunks;      /* record chunks used by the binned path                    */
+    uint64_t n_valid;       /* points that fell inside the window                       */
+    uint32_t n_tiles;       /* shared-memory tiles of the binned path                   */
+    uint32_t reserved[3];
+} lm_bev_stats;
+
+int         lm_bev_abi_version(void);
+const char *lm_bev_last_error(void);
+
+/* Bytes of device workspace lm_bev_rasterize needs for n_points points (256-B aligned). */
+int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, size_t *bytes);
+
+/* points_dev: n_points packed records (x, y, z, intensity) of 4 x f32 = one 16-byte float4
+ * each, 16-byte aligned, in the raster's local frame (the LAS read offset and the sidecar
+ * rotation/translation already removed; intensity = the LAS u16 value as a float, the
+ * record convention of read_las, reference baseline/datasets/laserlane_proposals.py:618-636). */
+int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
+                     void *workspace_dev, size_t workspace_bytes,
+                     const lm_bev_outputs *out, void *stream);
+
+/* dst = merge(dst, src) over rows [0,rows) of two accumulator sets whose planes are
+ * dst_plane_stride / src_plane_stride ELEMENTS apart (count, sums: add; max: max; min: min).
+ * This is the halo-merge law of strip sharding.                 */
+int lm_bev_acc_merge(uint32_t *dst_acc_dev, int64_t dst_plane_stride,
+                     const uint32_t *src_acc_dev, int64_t src_plane_stride,
+                     int32_t rows, int32_t width, void *stream);
+
+/* Accumulators -> requested outputs for rows [row_begin,row_end) of the window.  acc_dev
+ * is [LM_ACC_PLANES][p->height][p->width]; outputs are full-window buffers.            */
+int lm_bev_finalize(const lm_bev_params *p, const uint32_t *acc_dev,
+                    int32_t row_begin, int32_t row_end, const lm_bev_outputs *out, void *stream);
+
+/* Cut a [height][width][c] u8 mosaic into non-overlapping tile x tile crops (row-major crop
+ * order, ragged edges zero-filled = empty cells): crops_dev is [n_crops][tile][tile][c].
+ * tile = 1152 for cropped_tiff (reference configs/Proj_polyline_fpn_vit_vertex_2.py:38).  */
+int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, int32_t c,
+                      int32_t tile, uint8_t *crops_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM_BEV_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of include/lm_bev.h.  There is NO fallback: if the shared library is
+missing the import of any product entry point raises, and calls on a box without a GPU fail
+with the CUDA error the library reports."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+ABI_VERSION = 1
+ALGO_BINNED, ALGO_DIRECT = 0, 1
+DEV_ERR_POOL, DEV_ERR_CELL_OVERFLOW = 1, 2
+
+
+class LmBevParams(C.Structure):
+    _fields_ = [
+        ("height", C.c_int32), ("width", C.c_int32),
+        ("row0", C.c_int32), ("col0", C.c_int32),
+        ("bev_img_offset", C.c_float * 2),
+        ("img_reso", C.c_float * 2),
+        ("local_min_ele", C.c_float),
+        ("ele_reso", C.c_float),
+        ("inten_min", C.c_int32), ("inten_max", C.c_int32),
+        ("n_channels", C.c_int32),
+        ("channels", C.c_int32 * 4),
+    ]
+
+
+class LmBevOutputs(C.Structure):
+    _fields_ = [
+        ("image_dev", C.c_void_p),
+        ("count16_dev", C.c_void_p),
+        ("proj_dev", C.c_void_p),
+        ("acc_dev", C.c_void_p),
+        ("acc_band", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class LmBevStats(C.Structure):
+    _fields_ = [
+        ("error", C.c_uint32), ("n_chunks", C.c_uint32),
+        ("n_valid", C.c_uint64),
+        ("n_tiles", C.c_uint32), ("reserved", C.c_uint32 * 3),
+    ]
+
+
+SYMBOLS = {
+    "lm_bev_abi_version": (C.c_int, []),
+    "lm_bev_last_error": (C.c_char_p, []),
+    "lm_bev_workspace_bytes": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
+    "lm_bev_rasterize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
+                                   C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_bev_acc_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "lm_bev_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32,
+                                  C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_bev_crop_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class LmBevError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"liblm_bev error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """Load liblm_bev.so (once).  Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m lanemapping_b200.build` "
+                "(nvcc, sm_100a).  lanemapping_b200 has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        got = handle.lm_bev_abi_version()
+        if got != ABI_VERSION:
+            raise ImportError(f"liblm_bev ABI {got} != binding ABI {ABI_VERSION}: rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise LmBevError(code, lib().lm_bev_last_error().decode("utf-8", "replace"))
+
+
+def make_params(spec) -> LmBevParams:
+    p = LmBevParams()
+    p.height, p.width, p.row0, p.col0 = spec.height, spec.width, spec.row0, spec.col0
+    p.bev_img_offset[0], p.bev_img_offset[1] = spec.bev_img_offset
+    p.img_reso[0], p.img_reso[1] = spec.img_reso
+    p.local_min_ele, p.ele_reso = spec.local_min_ele, spec.ele_reso
+    p.inten_min, p.inten_max = spec.inten_min, spec.inten_max
+    p.n_channels = len(spec.channels)
+    for i, c in enumerate(spec.channels):
+        p.channels[i] = int(c)
+    return p

@@ -1,0 +1,200 @@
+"""PyTorch-facing host API of the BEV rasteriser.
+
+PyTorch is plumbing here: it owns device memory and streams.  All arithmetic runs in
+``csrc/liblm_bev.so`` through the C-ABI of ``include/lm_bev.h``; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .spec import ACC_PLANES, BevSpec
+
+ALGOS = {"binned": _cabi.ALGO_BINNED, "direct": _cabi.ALGO_DIRECT}
+OUTPUT_KEYS = ("image", "count16", "proj", "acc")
+
+
+def workspace_bytes(spec: BevSpec, n_points: int, algo: str = "binned") -> int:
+    p = _cabi.make_params(spec)
+    out = C.c_size_t(0)
+    _cabi.check(_cabi.lib().lm_bev_workspace_bytes(C.byref(p), int(n_points), ALGOS[algo], C.byref(out)))
+    return int(out.value)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class BevRasterizer:
+    """A spec + a reusable device workspace sized for ``max_points``.
+
+    ``outputs`` picks the buffers to produce: ``image`` u8 [H,W,C] (the cropped_tiff pixel
+    layout), ``count16`` u16 [H,W], ``proj`` f32 [C,H,W] (= the loader's
+    ``to_tensor(img).float()``, reference baseline/datasets/laserlane_proposals.py:88-89)
+    and ``acc`` u32 [6,H,W] raw accumulators (strip-halo merges).
+    """
+
+    def __init__(self, spec: BevSpec, max_points: int, device: torch.device | str = "cuda",
+                 algo: str = "binned", outputs: Iterable[str] = ("image",), acc_band: int = 0):
+        if algo not in ALGOS:
+            raise ValueError(f"algo must be one of {sorted(ALGOS)}")
+        outputs = tuple(outputs)
+        if not outputs or any(o not in OUTPUT_KEYS for o in outputs):
+            raise ValueError(f"outputs must be a non-empty subset of {OUTPUT_KEYS}")
+        if "count16" in outputs and not spec.count16:
+            raise ValueError("count16 output requested but spec.count16 is False")
+        self.spec = spec
+        self.algo = algo
+        self.outputs = outputs
+        self.acc_band = int(acc_band)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("lanemapping_b200 runs on CUDA devices only (no CPU fallback)")
+        self.max_points = int(max_points)
+        self._params = _cabi.make_params(spec)
+        self._lib = _cabi.lib()
+        self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo), dtype=torch.uint8,
+                                     device=self.device)
+
+    # -- buffers ----------------------------------------------------------------------------
+    def alloc_outputs(self) -> Dict[str, torch.Tensor]:
+        H, W, Cn = self.spec.height, self.spec.width, self.spec.n_channels
+        out: Dict[str, torch.Tensor] = {}
+        if "image" in self.outputs:
+            out["image"] = torch.empty((H, W, Cn), dtype=torch.uint8, device=self.device)
+        if "count16" in self.outputs:
+            out["count16"] = torch.empty((H, W), dtype=torch.uint16, device=self.device)
+        if "proj" in self.outputs:
+            out["proj"] = torch.empty((Cn, H, W), dtype=torch.float32, device=self.device)
+        if "acc" in self.outputs:
+            # rows outside the requested band are never written: start from the empty value
+            out["acc"] = torch.zeros((ACC_PLANES, H, W), dtype=torch.int32, device=self.device)
+        return out
+
+    # -- the call ---------------------------------------------------------------------------
+    def __call__(self, points: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None,
+                 stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+        """Enqueue one rasterisation of ``points`` (f32 [N,4] contiguous, on this device)."""
+        if points.device != self.workspace.device and points.device.index != self.workspace.device.index:
+            raise ValueError("points must live on the rasteriser's device")
+        if points.dtype != torch.float32 or points.dim() != 2 or points.shape[1] != 4 or not points.is_contiguous():
+            raise ValueError("points must be a contiguous float32 [N,4] tensor (x, y, z, intensity)")
+        n = int(points.shape[0])
+        if n > self.max_points:
+            raise ValueError(f"{n} points > max_points={self.max_points} this workspace was sized for")
+        if out is None:
+            out = self.alloc_outputs()
+        o = _cabi.LmBevOutputs()
+        o.image_dev = _ptr(out.get("image"))
+        o.count16_dev = _ptr(out.get("count16"))
+        o.proj_dev = _ptr(out.get("proj"))
+        o.acc_dev = _ptr(out.get("acc"))
+        o.acc_band = self.acc_band
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.lm_bev_rasterize(
+                C.byref(self._params), points.data_ptr() if n else None, n, ALGOS[self.algo],
+                self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream))
+        return out
+
+    def stats(self) -> dict:
+        """Device-side counters of the last call (synchronises)."""
+        raw = self.workspace[:C.sizeof(_cabi.LmBevStats)].cpu().numpy().tobytes()
+        s = _cabi.LmBevStats.from_buffer_copy(raw)
+        return {"error": int(s.error), "n_chunks": int(s.n_chunks), "n_valid": int(s.n_valid),
+                "n_tiles": int(s.n_tiles)}
+
+    def check_device_errors(self) -> None:
+        s = self.stats()
+        if s["error"] & _cabi.DEV_ERR_POOL:
+            raise RuntimeError("liblm_bev: record chunk pool exhausted (workspace too small)")
+        if s["error"] & _cabi.DEV_ERR_CELL_OVERFLOW:
+            raise RuntimeError("liblm_bev: a cell received >= 2^24 points; u32 sums may have wrapped")
+
+
+def rasterize(points: torch.Tensor, spec: BevSpec, algo: str = "binned",
+              outputs: Iterable[str] = ("image",)) -> Dict[str, torch.Tensor]:
+    """One-shot convenience wrapper (allocates a workspace for this call)."""
+    r = BevRasterizer(spec, int(points.shape[0]), device=points.device, algo=algo, outputs=outputs)
+    return r(points)
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers on finished rasters
+# ---------------------------------------------------------------------------------------------
+def acc_merge_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst <- merge(dst, src) for two accumulator sets [6,rows,W] (views into bigger [6,H,W]
+    buffers are fine as long as each plane's rows are contiguous)."""
+    if dst.shape != src.shape or dst.dim() != 3 or dst.shape[0] != ACC_PLANES:
+        raise ValueError("acc_merge_: expected two [6,rows,W] tensors of equal shape")
+    for t in (dst, src):
+        if t.stride(2) != 1 or t.stride(1) != t.shape[2] or t.dtype != torch.int32:
+            raise ValueError("acc_merge_: planes must be int32 with contiguous rows")
+    st = torch.cuda.current_stream(dst.device)
+    with torch.cuda.device(dst.device):
+        _cabi.check(_cabi.lib().lm_bev_acc_merge(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.stride(0),
+                                                 dst.shape[1], dst.shape[2], st.cuda_stream))
+    return dst
+
+
+def finalize_rows(spec: BevSpec, acc: torch.Tensor, row_begin: int, row_end: int,
+                  out: Dict[str, torch.Tensor]) -> None:
+    """Accumulators [6,H,W] -> the buffers in ``out`` for rows [row_begin,row_end)."""
+    if tuple(acc.shape) != (ACC_PLANES, spec.height, spec.width) or not acc.is_contiguous():
+        raise ValueError("finalize_rows: acc must be contiguous [6,H,W]")
+    p = _cabi.make_params(spec)
+    o = _cabi.LmBevOutputs()
+    o.image_dev = _ptr(out.get("image"))
+    o.count16_dev = _ptr(out.get("count16"))
+    o.proj_dev = _ptr(out.get("proj"))
+    st = torch.cuda.current_stream(acc.device)
+    with torch.cuda.device(acc.device):
+        _cabi.check(_cabi.lib().lm_bev_finalize(C.byref(p), acc.data_ptr(), int(row_begin), int(row_end),
+                                                C.byref(o), st.cuda_stream))
+
+
+def crop_tiles(image: torch.Tensor, tile: int = 1152) -> torch.Tensor:
+    """u8 [H,W,C] mosaic -> u8 [n_crops,tile,tile,C], row-major crop order, ragged edges zero."""
+    if image.dtype != torch.uint8 or image.dim() != 3 or not image.is_contiguous():
+        raise ValueError("crop_tiles: image must be contiguous uint8 [H,W,C]")
+    H, W, Cn = image.shape
+    n = (-(-H // tile)) * (-(-W // tile))
+    crops = torch.empty((n, tile, tile, Cn), dtype=torch.uint8, device=image.device)
+    st = torch.cuda.current_stream(image.device)
+    with torch.cuda.device(image.device):
+        _cabi.check(_cabi.lib().lm_bev_crop_tiles(image.data_ptr(), H, W, Cn, tile, crops.data_ptr(), st.cuda_stream))
+    return crops
+
+
+class HostRasterizer:
+    """End-to-end entry with HOST buffers: pinned staging, H2D copy, kernels, D2H copy.
+
+    This is the call an offline converter makes per file (see convert_data.py in this
+    package) and what bench.py times as ``e2e``.
+    """
+
+    def __init__(self, spec: BevSpec, max_points: int, device: torch.device | str = "cuda",
+                 algo: str = "binned", outputs: Iterable[str] = ("image",)):
+        self.raster = BevRasterizer(spec, max_points, device=device, algo=algo, outputs=outputs)
+        self.dev_points = torch.empty((max_points, 4), dtype=torch.float32, device=self.raster.device)
+        self.dev_out = self.raster.alloc_outputs()
+        self.host_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.dev_out.items()}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def __call__(self, points_host: torch.Tensor) -> Dict[str, np.ndarray]:
+        """points_host: float32 [N,4] CPU tensor (pinned for full copy speed)."""
+        n = int(points_host.shape[0])
+        dev = self.dev_points[:n]
+        dev.copy_(points_host, non_blocking=True)
+        self.raster(dev, out=self.dev_out)
+        for k, v in self.dev_out.items():
+            self.host_out[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(self.raster.device).synchronize()
+        self.h2d_bytes = n * 16
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.dev_out.values())
+        return {k: v.numpy() for k, v in self.host_out.items()}

@@ -1,0 +1,843 @@
+// lm_bev.cu -- hand-written sm_100a kernels + the C-ABI of include/lm_bev.h.
+//
+// Pipeline of the product path (LM_ALGO_BINNED), all integer after the per-point keys:
+//
+//   bin_points_kernel     one coalesced float4 pass over the packed point records: per point
+//                         the cell key and the quantised intensity/height are packed into ONE
+//                         32-bit record [cell-in-tile:14 | iq:8 | zq:8]; every CTA counting-sorts
+//                         its batch by tile in shared memory and appends each tile's run to a
+//                         CTA-private chunk of that tile (chunks come from a bump-allocated pool),
+//                         so global writes are contiguous runs and no pre-count pass is needed.
+//   scan_tiles/index      tiny: per-tile chunk lists from the chunk side table.
+//   reduce_tiles_kernel   persistent CTAs, one tile at a time: stream the tile's chunks, reduce
+//                         into a shared-memory accumulator tile with integer atomics
+//                         (count/sum add, max, min), derive the u8 channels in place and write the
+//                         tile out coalesced (u8 HWC image, u16 count plane, f32 CHW proj, raw acc).
+//
+// HBM traffic: 16 B/pt read + 4 B/pt written + 4 B/pt read + output  (DESIGN.md section 4).
+// No tensor cores: nothing here is a dense contraction.
+//
+// Bit-exactness: all float steps are single IEEE-754 binary32 operations (__fsub_rn/__fdiv_rn,
+// floorf, rintf); compile with -fmad=false and never with -use_fast_math.
+#include "lm_bev.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_W_LOG2 = 7;            // shared-memory tile: 128 cols x (128 | 64) rows
+constexpr int TILE_W = 1 << TILE_W_LOG2;
+constexpr int CHUNK_RECS = 512;           // records per pool chunk (2 KB)
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_PPT = 8;                // points per thread per batch
+constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
+constexpr int MAX_BIN_CTAS = 148 * 4;     // sizing constant of the workspace (B200: 148 SMs)
+constexpr int RED_THREADS = 512;
+constexpr int MAX_TILES = 40000;          // limit of bin_points' shared-memory histogram
+constexpr uint32_t INVALID_U32 = 0xFFFFFFFFu;
+
+// accumulator planes held in shared memory by reduce_tiles (bit mask)
+enum : int { M_CNT = 1, M_SUMI = 2, M_SUMZ = 4, M_MAXI = 8, M_MINZ = 16, M_MAXZ = 32, M_ALL = 63 };
+
+__host__ __device__ constexpr int popc6(int m) {
+    return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1) + ((m >> 4) & 1) + ((m >> 5) & 1);
+}
+// index of plane `bit` inside the packed plane list of `mask`
+__host__ __device__ constexpr int plane_of(int mask, int bit) { return popc6(mask & (bit - 1)); }
+
+struct KParams {
+    int H, W, row0, col0;
+    float off0, off1, reso0, reso1, zmin, zreso;
+    float row_lo, row_hi, col_lo, col_hi;
+    float imin_f, imax_f;
+    int imin;
+    unsigned long long imagic;  // floor(2^40 / (imax-imin)) + 1: exact n/d for n < 2^24
+    int nch;
+    int ch[4];
+    int tile_h_log2, tiles_x, tiles_y, T;
+};
+
+struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
+    unsigned int pool_cursor;   // chunks handed out so far (chunk ids are cursor+1: id 0 = none)
+    unsigned int tile_counter;  // reduce_tiles scheduler
+    unsigned int pad[6];
+};
+
+struct Ws {                  // device pointers into the caller's workspace
+    lm_bev_stats *stats;
+    Ctl *ctl;
+    uint32_t *tile_nchunks;  // [T]
+    uint32_t *tile_first;    // [T]
+    uint32_t *tile_cursor;   // [T]
+    uint2 *state;            // [MAX_BIN_CTAS][T] {cur chunk id, fill}
+    uint2 *chunk_meta;       // [P] {tile, count}
+    uint32_t *chunk_index;   // [P]
+    uint32_t *pool;          // [P][CHUNK_RECS]
+    uint32_t *acc;           // direct path: [6][H][W]
+    uint32_t pool_chunks;    // P
+};
+
+struct Outs {
+    uint8_t *image;
+    uint16_t *count16;
+    float *proj;
+    uint32_t *acc;
+    int acc_band;
+};
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-point quantisation (the spec; oracle/bev_oracle.py::quantise_points restates it)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool quantise(const float4 p, const KParams &k, int &lrow, int &lcol,
+                                         uint32_t &iq, uint32_t &zq) {
+    // inverse of reference baseline/utils/coor_img2pc.py:136-139 (row <-> x, col <-> y)
+    const float rf = floorf(__fdiv_rn(__fsub_rn(p.x, k.off0), k.reso0));
+    const float cf = floorf(__fdiv_rn(__fsub_rn(p.y, k.off1), k.reso1));
+    const bool valid = (rf >= k.row_lo) && (rf < k.row_hi) && (cf >= k.col_lo) && (cf < k.col_hi);  // NaN -> false
+    lrow = (int)rf - k.row0;
+    lcol = (int)cf - k.col0;
+    // inverse of coor_img2pc.py:150, round-half-even; NaN -> 0 through fmaxf
+    float zf = rintf(__fdiv_rn(__fsub_rn(p.z, k.zmin), k.zreso));
+    zf = fminf(fmaxf(zf, 0.0f), 255.0f);
+    zq = (uint32_t)(int)zf;
+    // clip of reference baseline/datasets/laserlane_proposals.py:626-628, then u8 mapping
+    const float ic = fminf(fmaxf(p.w, k.imin_f), k.imax_f);
+    const uint32_t n = (uint32_t)((int)ic - k.imin) * 255u;      // < 2^24
+    iq = (uint32_t)(((unsigned long long)n * k.imagic) >> 40);    // == n / (imax-imin)
+    return valid;
+}
+
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+
+// ------------------------------------------------------------------------------------------
+// channel derivation shared by every finishing path
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t channel_value(int ch, uint32_t cnt, uint32_t sum_i, uint32_t sum_z,
+                                                  uint32_t max_i, uint32_t min_z, uint32_t max_z) {
+    switch (ch) {
+        case LM_CH_MAX_I: return max_i;
+        case LM_CH_MEAN_I: return cnt ? (uint32_t)(((unsigned long long)sum_i + (cnt >> 1)) / cnt) : 0u;
+        case LM_CH_MIN_Z: return cnt ? min_z : 0u;
+        case LM_CH_MAX_Z: return max_z;
+        case LM_CH_MEAN_Z: return cnt ? (uint32_t)(((unsigned long long)sum_z + (cnt >> 1)) / cnt) : 0u;
+        case LM_CH_DENSITY: return cnt < 255u ? cnt : 255u;
+    }
+    return 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// LM_ALGO_DIRECT: global atomics (cross-check path; also finishes merged halo bands)
+// ------------------------------------------------------------------------------------------
+__global__ void acc_init_kernel(uint32_t *acc, size_t cells) {
+    const size_t n = cells * LM_ACC_PLANES;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc[i] = (i / cells == LM_ACC_MIN_Z) ? INVALID_U32 : 0u;
+}
+
+__global__ void __launch_bounds__(256) direct_accumulate_kernel(KParams kp, const float4 *__restrict__ pts,
+                                                                long long n, uint32_t *acc, lm_bev_stats *stats) {
+    const size_t cells = (size_t)kp.H * kp.W;
+    unsigned long long nvalid = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int r, c;
+        uint32_t iq, zq;
+        if (!quantise(ld_stream(pts + i), kp, r, c, iq, zq)) continue;
+        const size_t cell = (size_t)r * kp.W + c;
+        const uint32_t old = atomicAdd(&acc[LM_ACC_COUNT * cells + cell], 1u);
+        if (old >= (1u << 24)) atomicOr(&stats->error, (uint32_t)LM_DEV_ERR_CELL_OVERFLOW);
+        atomicAdd(&acc[LM_ACC_SUM_I * cells + cell], iq);
+        atomicAdd(&acc[LM_ACC_SUM_Z * cells + cell], zq);
+        atomicMax(&acc[LM_ACC_MAX_I * cells + cell], iq);
+        atomicMin(&acc[LM_ACC_MIN_Z * cells + cell], zq);
+        atomicMax(&acc[LM_ACC_MAX_Z * cells + cell], zq);
+        ++nvalid;
+    }
+    for (int o = 16; o; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd((unsigned long long *)&stats->n_valid, nvalid);
+}
+
+// acc [6][H][W] -> outputs, rows [r0,r1)
+__global__ void finalize_kernel(KParams kp, const uint32_t *__restrict__ acc, int r0, int r1, Outs out) {
+    const size_t cells = (size_t)kp.H * kp.W;
+    const size_t lo = (size_t)r0 * kp.W, hi = (size_t)r1 * kp.W;
+    for (size_t cell = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; cell < hi;
+         cell += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t cnt = acc[LM_ACC_COUNT * cells + cell];
+        const uint32_t si = acc[LM_ACC_SUM_I * cells + cell], sz = acc[LM_ACC_SUM_Z * cells + cell];
+        const uint32_t mi = acc[LM_ACC_MAX_I * cells + cell], nz = acc[LM_ACC_MIN_Z * cells + cell];
+        const uint32_t xz = acc[LM_ACC_MAX_Z * cells + cell];
+        for (int c = 0; c < kp.nch; ++c) {
+            const uint32_t v = channel_value(kp.ch[c], cnt, si, sz, mi, nz, xz);
+            if (out.image) out.image[cell * kp.nch + c] = (uint8_t)v;
+            if (out.proj) out.proj[(size_t)c * cells + cell] = __fdiv_rn((float)v, 255.0f);
+        }
+        if (out.count16) out.count16[cell] = (uint16_t)(cnt < 65535u ? cnt : 65535u);
+    }
+}
+
+__global__ void acc_merge_kernel(uint32_t *dst, long long dstride, const uint32_t *__restrict__ src,
+                                 long long sstride, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        dst[LM_ACC_COUNT * dstride + i] += src[LM_ACC_COUNT * sstride + i];
+        dst[LM_ACC_SUM_I * dstride + i] += src[LM_ACC_SUM_I * sstride + i];
+        dst[LM_ACC_SUM_Z * dstride + i] += src[LM_ACC_SUM_Z * sstride + i];
+        dst[LM_ACC_MAX_I * dstride + i] = max(dst[LM_ACC_MAX_I * dstride + i], src[LM_ACC_MAX_I * sstride + i]);
+        dst[LM_ACC_MIN_Z * dstride + i] = min(dst[LM_ACC_MIN_Z * dstride + i], src[LM_ACC_MIN_Z * sstride + i]);
+        dst[LM_ACC_MAX_Z * dstride + i] = max(dst[LM_ACC_MAX_Z * dstride + i], src[LM_ACC_MAX_Z * sstride + i]);
+    }
+}
+
+__global__ void crop_tiles_kernel(const uint8_t *__restrict__ img, int H, int W, int C, int tile, int ncx,
+                                  uint8_t *__restrict__ crops, size_t total) {
+    const size_t row_bytes = (size_t)tile * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i % row_bytes;           // byte inside the crop row
+        const size_t rr = i / row_bytes;          // crop * tile + r
+        const int r = (int)(rr % tile);
+        const int crop = (int)(rr / tile);
+        const int gy = (crop / ncx) * tile + r;
+        const size_t gxb = (size_t)(crop % ncx) * row_bytes + b;   // byte inside the mosaic row
+        crops[i] = (gy < H && gxb < (size_t)W * C) ? img[(size_t)gy * W * C + gxb] : (uint8_t)0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LM_ALGO_BINNED stage 1: bin_points
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_t count, uint32_t tile) {
+    ws.chunk_meta[id] = make_uint2(tile, count);
+    atomicAdd(&ws.tile_nchunks[tile], 1u);
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
+                                                                 long long n, Ws ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = kp.T;
+    const int D = T < BIN_BATCH ? T : BIN_BATCH;              // max tiles one batch can touch
+    uint4 *desc = reinterpret_cast<uint4 *>(smem_raw);                       // [D] {start, dst0, room, dst1}
+    uint2 *sorted = reinterpret_cast<uint2 *>(desc + D);                     // [BIN_BATCH] {rec, desc idx}
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sorted + BIN_BATCH);       // [T]
+    uint32_t *touched = hist + T;                                            // [D]
+    __shared__ uint32_t s_cnt[2][2];                                         // [parity]{n_touched, cursor}
+
+    const int tid = threadIdx.x;
+    for (int t = tid; t < T; t += BIN_THREADS) hist[t] = 0;
+    if (tid < 4) (&s_cnt[0][0])[tid] = 0;
+    __syncthreads();
+
+    const long long nb = (n + BIN_BATCH - 1) / BIN_BATCH;
+    const long long b0 = nb * blockIdx.x / gridDim.x, b1 = nb * (blockIdx.x + 1) / gridDim.x;
+    uint2 *my_state = ws.state + (size_t)blockIdx.x * T;
+    unsigned long long my_valid = 0;   // thread 0 only
+
+    for (long long b = b0; b < b1; ++b) {
+        const int par = (int)((b - b0) & 1);
+        const long long base = b * BIN_BATCH;
+        float4 p[BIN_PPT];
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            const long long idx = base + j * BIN_THREADS + tid;
+            p[j] = idx < n ? ld_stream(pts + idx) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        }
+        uint32_t rec[BIN_PPT], tl[BIN_PPT], rk[BIN_PPT];
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            int r, c;
+            uint32_t iq, zq;
+            if (quantise(p[j], kp, r, c, iq, zq)) {
+                const uint32_t t = (uint32_t)((r >> kp.tile_h_log2) * kp.tiles_x + (c >> TILE_W_LOG2));
+                const uint32_t cell = (uint32_t)(((r & ((1 << kp.tile_h_log2) - 1)) << TILE_W_LOG2) | (c & (TILE_W - 1)));
+                rec[j] = (cell << 16) | (iq << 8) | zq;
+                tl[j] = t;
+                rk[j] = atomicAdd(&hist[t], 1u);
+                if (rk[j] == 0) touched[atomicAdd(&s_cnt[par][0], 1u)] = t;
+            } else {
+                tl[j] = INVALID_U32;
+            }
+        }
+        __syncthreads();
+        // ---- one thread per touched tile: reserve a run in the sort buffer and in the tile's chunks
+        const int nt = (int)s_cnt[par][0];
+        for (int k = tid; k < nt; k += BIN_THREADS) {
+            const uint32_t t = touched[k];
+            const uint32_t c = hist[t];
+            const uint32_t start = atomicAdd(&s_cnt[par][1], c);
+            uint2 st = __ldcg(&my_state[t]);
+            uint32_t cur = st.x, fill = st.y;
+            const uint32_t room = cur ? (uint32_t)CHUNK_RECS - fill : 0u;
+            const uint32_t dst0 = cur * (uint32_t)CHUNK_RECS + fill;
+            uint32_t dst1 = INVALID_U32;
+            if (c > room) {
+                const uint32_t rest = c - room;
+                const uint32_t n_new = (rest + CHUNK_RECS - 1) / CHUNK_RECS;
+                const uint32_t first = atomicAdd(&ws.ctl->pool_cursor, n_new) + 1u;   // ids start at 1
+                if (first + n_new > ws.pool_chunks) {
+                    atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
+                    fill = cur ? (uint32_t)CHUNK_RECS : 0u;     // records beyond `room` are dropped
+                } else {
+                    if (cur) publish_chunk(ws, cur, CHUNK_RECS, t);
+                    for (uint32_t q = 0; q + 1 < n_new; ++q) publish_chunk(ws, first + q, CHUNK_RECS, t);
+                    cur = first + n_new - 1;
+                    fill = rest - (n_new - 1) * CHUNK_RECS;
+                    dst1 = first * (uint32_t)CHUNK_RECS;
+                }
+            } else {
+                fill += c;
+            }
+            __stcg(&my_state[t], make_uint2(cur, fill));
+            desc[k] = make_uint4(start, dst0, room, dst1);
+            hist[t] = (uint32_t)k;           // tile -> descriptor index for the scatter below
+        }
+        if (tid == 0) { s_cnt[par ^ 1][0] = 0; s_cnt[par ^ 1][1] = 0; }
+        __syncthreads();
+        // ---- scatter records into tile-sorted order (shared memory)
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            if (tl[j] != INVALID_U32) {
+                const uint32_t k = hist[tl[j]];
+                sorted[desc[k].x + rk[j]] = make_uint2(rec[j], k);
+            }
+        }
+        __syncthreads();
+        // ---- coalesced write-out: consecutive threads -> consecutive records of a run
+        const int nv = (int)s_cnt[par][1];
+        for (int i = tid; i < nv; i += BIN_THREADS) {
+            const uint2 e = sorted[i];
+            const uint4 d = desc[e.y];
+            const uint32_t off = (uint32_t)i - d.x;
+            if (off < d.z) ws.pool[d.y + off] = e.x;
+            else if (d.w != INVALID_U32) ws.pool[d.w + (off - d.z)] = e.x;
+        }
+        for (int k = tid; k < nt; k += BIN_THREADS) hist[touched[k]] = 0;
+        if (tid == 0) my_valid += (unsigned long long)nv;
+        __syncthreads();
+    }
+    // ---- retire this CTA's open chunks
+    for (int t = tid; t < T; t += BIN_THREADS) {
+        const uint2 st = __ldcg(&my_state[t]);
+        if (st.x) publish_chunk(ws, st.x, st.y, (uint32_t)t);
+    }
+    if (tid == 0 && my_valid) atomicAdd((unsigned long long *)&ws.stats->n_valid, my_valid);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 2: per-tile chunk lists
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, int T) {
+    __shared__ uint32_t s_part[1024];
+    __shared__ uint32_t s_err;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_err = ws.stats->error & LM_DEV_ERR_POOL;
+        const uint32_t used = ws.ctl->pool_cursor;
+        ws.stats->n_chunks = used < ws.pool_chunks ? used : ws.pool_chunks;
+        ws.stats->n_tiles = (uint32_t)T;
+    }
+    __syncthreads();
+    const int per = (T + 1023) / 1024;
+    const int lo = tid * per, hi = min(T, lo + per);
+    if (s_err) {   // pool exhausted: publish an empty raster instead of reading half-built lists
+        for (int t = lo; t < hi; ++t) ws.tile_nchunks[t] = 0;
+    }
+    uint32_t sum = 0;
+    for (int t = lo; t < hi; ++t) sum += ws.tile_nchunks[t];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan
+        const uint32_t v = tid >= o ? s_part[tid - o] : 0u;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+    for (int t = lo; t < hi; ++t) {
+        ws.tile_first[t] = run;
+        run += ws.tile_nchunks[t];
+    }
+}
+
+__global__ void index_chunks_kernel(Ws ws) {
+    if (ws.stats->error & LM_DEV_ERR_POOL) return;
+    const uint32_t used = ws.ctl->pool_cursor;    // ids 1..used
+    for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= used; id += gridDim.x * blockDim.x) {
+        const uint32_t t = ws.chunk_meta[id].x;
+        const uint32_t slot = ws.tile_first[t] + atomicAdd(&ws.tile_cursor[t], 1u);
+        ws.chunk_index[slot] = id;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 3: reduce_tiles
+// ------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void write_image_rows(const uint32_t *__restrict__ packed, uint8_t *image, int W,
+                                                 int grow0, int gcol0, int nrows, int ncols, int tid) {
+    // tile row = ncols*C contiguous bytes; each thread emits one aligned 32-bit word when possible
+    const int bytes = ncols * C;
+    const size_t row_stride = (size_t)W * C;
+    uint8_t *base = image + ((size_t)grow0 * W + gcol0) * C;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 3) == 0) && ((row_stride & 3) == 0);
+    if (aligned) {
+        const int words = bytes >> 2;
+        for (int it = tid; it < nrows * words; it += RED_THREADS) {
+            const int lr = it / words, w = it - lr * words;
+            uint32_t v = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int bi = 4 * w + e;
+                const int cell = bi / C, ch = bi - cell * C;
+                v |= ((packed[(lr << TILE_W_LOG2) + cell] >> (8 * ch)) & 0xFFu) << (8 * e);
+            }
+            *reinterpret_cast<uint32_t *>(base + lr * row_stride + 4 * w) = v;
+        }
+        const int tail = bytes & 3;
+        if (tail) {
+            for (int it = tid; it < nrows * tail; it += RED_THREADS) {
+                const int lr = it / tail, bi = (bytes & ~3) + (it - lr * tail);
+                const int cell = bi / C, ch = bi - cell * C;
+                base[lr * row_stride + bi] = (uint8_t)(packed[(lr << TILE_W_LOG2) + cell] >> (8 * ch));
+            }
+        }
+    } else {
+        for (int it = tid; it < nrows * bytes; it += RED_THREADS) {
+            const int lr = it / bytes, bi = it - lr * bytes;
+            const int cell = bi / C, ch = bi - cell * C;
+            base[lr * row_stride + bi] = (uint8_t)(packed[(lr << TILE_W_LOG2) + cell] >> (8 * ch));
+        }
+    }
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(RED_THREADS, 1) reduce_tiles_kernel(KParams kp, Ws ws, Outs out) {
+    constexpr int NW = popc6(MASK);
+    extern __shared__ __align__(16) uint32_t acc[];      // [NW][cells]; plane 0/1 reused as packed/count16
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TH = 1 << kp.tile_h_log2;
+    const int cells = TH << TILE_W_LOG2;
+    uint32_t *a_cnt = acc + plane_of(MASK, M_CNT) * cells;
+    uint32_t *a_sumi = acc + plane_of(MASK, M_SUMI) * cells;
+    uint32_t *a_sumz = acc + plane_of(MASK, M_SUMZ) * cells;
+    uint32_t *a_maxi = acc + plane_of(MASK, M_MAXI) * cells;
+    uint32_t *a_minz = acc + plane_of(MASK, M_MINZ) * cells;   // holds max(256 - zq): 0 = empty
+    uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
+    uint32_t *packed = acc;                                      // plane 0 after the finish step
+    uint32_t *cnt16 = acc + cells;                               // plane 1 after the finish step (NW >= 2)
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = (int)atomicAdd(&ws.ctl->tile_counter, 1u);
+        __syncthreads();
+        const int t = s_tile;
+        if (t >= kp.T) break;
+        const int trow = t / kp.tiles_x, tcol = t - trow * kp.tiles_x;
+        const int grow0 = trow << kp.tile_h_log2, gcol0 = tcol << TILE_W_LOG2;
+        const int nrows = min(TH, kp.H - grow0), ncols = min(TILE_W, kp.W - gcol0);
+        const uint32_t nchunks = ws.tile_nchunks[t];
+        const uint32_t first = ws.tile_first[t];
+        const bool want_raw = out.acc != nullptr &&
+                              (out.acc_band <= 0 || grow0 < out.acc_band || grow0 + nrows > kp.H - out.acc_band);
+
+        // ---- zero the accumulator tile
+        {
+            uint4 *a4 = reinterpret_cast<uint4 *>(acc);
+            const int n4 = NW * cells / 4;
+            for (int i = tid; i < n4; i += RED_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+
+        // ---- stream the tile's chunks: one chunk per warp, integer atomics in shared memory
+        for (uint32_t c = warp; c < nchunks; c += RED_THREADS / 32) {
+            const uint32_t id = ws.chunk_index[first + c];
+            const uint32_t cnt = ws.chunk_meta[id].y;
+            const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)id * CHUNK_RECS);
+            constexpr int V = CHUNK_RECS / 128;      // uint4 loads per lane per chunk
+            uint4 v[V];
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                v[q] = (uint32_t)((q * 32 + lane) * 4) < cnt ? __ldcs(src + q * 32 + lane) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const uint32_t r4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if ((uint32_t)((q * 32 + lane) * 4 + e) < cnt) {
+                        const uint32_t rec = r4[e];
+                        const uint32_t cell = rec >> 16, iq = (rec >> 8) & 0xFFu, zq = rec & 0xFFu;
+                        if (MASK & M_CNT) atomicAdd(&a_cnt[cell], 1u);
+                        if (MASK & M_SUMI) atomicAdd(&a_sumi[cell], iq);
+                        if (MASK & M_SUMZ) atomicAdd(&a_sumz[cell], zq);
+                        if (MASK & M_MAXI) atomicMax(&a_maxi[cell], iq);
+                        if (MASK & M_MINZ) atomicMax(&a_minz[cell], 256u - zq);
+                        if (MASK & M_MAXZ) atomicMax(&a_maxz[cell], zq);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- finish: raw planes out (halo tiles), then channels packed in place
+        const size_t gcells = (size_t)kp.H * kp.W;
+        bool overflow = false;
+        for (int cell = tid; cell < cells; cell += RED_THREADS) {
+            const int lr = cell >> TILE_W_LOG2, lc = cell & (TILE_W - 1);
+            const uint32_t cnt = (MASK & M_CNT) ? a_cnt[cell] : 0u;
+            const uint32_t si = (MASK & M_SUMI) ? a_sumi[cell] : 0u;
+            const uint32_t sz = (MASK & M_SUMZ) ? a_sumz[cell] : 0u;
+            const uint32_t mi = (MASK & M_MAXI) ? a_maxi[cell] : 0u;
+            const uint32_t nzr = (MASK & M_MINZ) ? a_minz[cell] : 0u;
+            const uint32_t xz = (MASK & M_MAXZ) ? a_maxz[cell] : 0u;
+            const uint32_t nz = nzr ? 256u - nzr : 0u;
+            overflow |= cnt >= (1u << 24);
+            const bool inside = lr < nrows && lc < ncols;
+            if (want_raw && inside) {
+                const size_t g = (size_t)(grow0 + lr) * kp.W + gcol0 + lc;
+                out.acc[LM_ACC_COUNT * gcells + g] = cnt;
+                out.acc[LM_ACC_SUM_I * gcells + g] = si;
+                out.acc[LM_ACC_SUM_Z * gcells + g] = sz;
+                out.acc[LM_ACC_MAX_I * gcells + g] = mi;
+                out.acc[LM_ACC_MIN_Z * gcells + g] = nzr ? nz : INVALID_U32;
+                out.acc[LM_ACC_MAX_Z * gcells + g] = xz;
+            }
+            uint32_t pk = 0;
+            for (int c = 0; c < kp.nch; ++c) {
+                // nz is already 0 for an empty cell, with or without a count plane
+                pk |= channel_value(kp.ch[c], kp.ch[c] == LM_CH_MIN_Z ? 1u : cnt, si, sz, mi, nz, xz) << (8 * c);
+            }
+            if (out.proj && inside) {
+                for (int c = 0; c < kp.nch; ++c)
+                    out.proj[((size_t)c * kp.H + grow0 + lr) * kp.W + gcol0 + lc] =
+                        __fdiv_rn((float)((pk >> (8 * c)) & 0xFFu), 255.0f);
+            }
+            packed[cell] = pk;
+            if (NW >= 2) cnt16[cell] = cnt < 65535u ? cnt : 65535u;
+        }
+        if (overflow) atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_CELL_OVERFLOW);
+        __syncthreads();
+
+        // ---- coalesced tile write-out
+        if (out.image) {
+            switch (kp.nch) {
+                case 1: write_image_rows<1>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
+                case 2: write_image_rows<2>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
+                case 3: write_image_rows<3>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
+                default: write_image_rows<4>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
+            }
+        }
+        if (NW >= 2 && out.count16) {
+            for (int it = tid; it < nrows * ncols; it += RED_THREADS) {
+                const int lr = it / ncols, lc = it - lr * ncols;
+                out.count16[(size_t)(grow0 + lr) * kp.W + gcol0 + lc] = (uint16_t)cnt16[(lr << TILE_W_LOG2) + lc];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int needed_mask(const lm_bev_params *p, bool count16, bool raw) {
+    if (raw) return M_ALL;
+    int m = 0;
+    for (int c = 0; c < p->n_channels; ++c) {
+        switch (p->channels[c]) {
+            case LM_CH_MAX_I: m |= M_MAXI; break;
+            case LM_CH_MEAN_I: m |= M_SUMI | M_CNT; break;
+            case LM_CH_MIN_Z: m |= M_MINZ; break;
+            case LM_CH_MAX_Z: m |= M_MAXZ; break;
+            case LM_CH_MEAN_Z: m |= M_SUMZ | M_CNT; break;
+            case LM_CH_DENSITY: m |= M_CNT; break;
+        }
+    }
+    if (count16) m |= M_CNT;
+    return m;
+}
+
+// instantiated accumulator sets; the smallest superset of the needed mask is used
+constexpr int K_MASKS[] = {M_MAXI, M_CNT | M_MAXI, M_CNT | M_SUMZ | M_MAXI,
+                           M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ, M_ALL};
+int pick_mask(int need, bool count16) {
+    for (int m : K_MASKS)
+        if ((m & need) == need && !(count16 && popc6(m) < 2)) return m;
+    return M_ALL;
+}
+int tile_h_log2_for(int mask) { return popc6(mask) <= 3 ? 7 : 6; }
+
+int validate(const lm_bev_params *p) {
+    if (!p) return fail(LM_ERR_INVALID, "params is NULL");
+    if (p->height <= 0 || p->width <= 0) return fail(LM_ERR_INVALID, "height/width must be positive");
+    if (p->n_channels < 1 || p->n_channels > 4) return fail(LM_ERR_INVALID, "n_channels must be 1..4");
+    for (int c = 0; c < p->n_channels; ++c)
+        if (p->channels[c] < 0 || p->channels[c] >= LM_CH__COUNT) return fail(LM_ERR_INVALID, "unknown channel id %d", p->channels[c]);
+    if (!(p->img_reso[0] > 0.f) || !(p->img_reso[1] > 0.f) || !(p->ele_reso > 0.f))
+        return fail(LM_ERR_INVALID, "resolutions must be positive");
+    if (p->inten_min < 0 || p->inten_max > 65535 || p->inten_min >= p->inten_max)
+        return fail(LM_ERR_INVALID, "need 0 <= inten_min < inten_max <= 65535");
+    const long long lim = 1ll << 24;
+    auto absll = [](long long v) { return v < 0 ? -v : v; };
+    if (absll(p->row0) + p->height >= lim || absll(p->col0) + p->width >= lim)
+        return fail(LM_ERR_INVALID, "window exceeds the exact-float index range 2^24");
+    return LM_OK;
+}
+
+KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
+    KParams k;
+    k.H = p->height; k.W = p->width; k.row0 = p->row0; k.col0 = p->col0;
+    k.off0 = p->bev_img_offset[0]; k.off1 = p->bev_img_offset[1];
+    k.reso0 = p->img_reso[0]; k.reso1 = p->img_reso[1];
+    k.zmin = p->local_min_ele; k.zreso = p->ele_reso;
+    k.row_lo = (float)p->row0; k.row_hi = (float)(p->row0 + p->height);
+    k.col_lo = (float)p->col0; k.col_hi = (float)(p->col0 + p->width);
+    k.imin_f = (float)p->inten_min; k.imax_f = (float)p->inten_max; k.imin = p->inten_min;
+    const unsigned long long d = (unsigned long long)(p->inten_max - p->inten_min);
+    k.imagic = d == 1 ? (1ull << 40) : ((1ull << 40) / d + 1ull);
+    k.nch = p->n_channels;
+    for (int c = 0; c < 4; ++c) k.ch[c] = c < p->n_channels ? p->channels[c] : 0;
+    k.tile_h_log2 = tile_h_log2;
+    k.tiles_x = (p->width + TILE_W - 1) >> TILE_W_LOG2;
+    k.tiles_y = (p->height + (1 << tile_h_log2) - 1) >> tile_h_log2;
+    k.T = k.tiles_x * k.tiles_y;
+    return k;
+}
+
+struct Layout {
+    size_t off_ctl, off_nchunks, off_first, off_cursor, off_state, zero_bytes;
+    size_t off_meta, off_index, off_pool, off_acc, total;
+    uint32_t pool_chunks;
+    int bin_ctas;
+};
+
+int bin_ctas_for(long long n) {
+    const long long nb = (n + BIN_BATCH - 1) / BIN_BATCH;
+    return (int)(nb < 1 ? 1 : (nb < MAX_BIN_CTAS ? nb : MAX_BIN_CTAS));
+}
+
+// Binned workspace: [stats | ctl | tile tables | per-CTA open-chunk state] (zeroed per call)
+//                   [chunk side table | chunk index | record pool]
+int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L) {
+    memset(L, 0, sizeof(*L));
+    size_t o = 0;
+    o = align_up(o + sizeof(lm_bev_stats), 64);
+    L->off_ctl = o; o = align_up(o + sizeof(Ctl), 256);
+    if (algo == LM_ALGO_DIRECT) {
+        L->zero_bytes = o;
+        L->off_acc = o;
+        o += (size_t)LM_ACC_PLANES * p->height * p->width * sizeof(uint32_t);
+        L->total = align_up(o, 256);
+        return LM_OK;
+    }
+    L->bin_ctas = bin_ctas_for(n);
+    L->off_nchunks = o; o = align_up(o + (size_t)T * 4, 256);
+    L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
+    L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
+    L->off_state = o;   o = align_up(o + (size_t)L->bin_ctas * T * sizeof(uint2), 256);
+    L->zero_bytes = o;
+    const unsigned long long chunks = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS) +
+                                      (unsigned long long)L->bin_ctas * T + 2ull;
+    if (chunks * CHUNK_RECS >= (1ull << 32))
+        return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^32 records: shard the call (fewer points or a smaller row window)");
+    L->pool_chunks = (uint32_t)chunks;
+    L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
+    L->off_index = o; o = align_up(o + (size_t)chunks * 4, 256);
+    L->off_pool = o;  o = align_up(o + (size_t)chunks * CHUNK_RECS * 4, 256);
+    L->total = o;
+    return LM_OK;
+}
+
+size_t bin_smem_bytes(int T) {
+    const int D = T < BIN_BATCH ? T : BIN_BATCH;
+    return (size_t)D * sizeof(uint4) + (size_t)BIN_BATCH * sizeof(uint2) + (size_t)T * 4 + (size_t)D * 4;
+}
+
+template <int MASK>
+cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sms, cudaStream_t st) {
+    const size_t smem = (size_t)popc6(MASK) * ((size_t)TILE_W << kp.tile_h_log2) * 4;
+    cudaError_t e = cudaFuncSetAttribute(reduce_tiles_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK>, RED_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    const int grid = kp.T < sms * occ ? kp.T : sms * occ;
+    reduce_tiles_kernel<MASK><<<grid, RED_THREADS, smem, st>>>(kp, ws, o);
+    return cudaGetLastError();
+}
+
+int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int lm_bev_abi_version(void) { return LM_BEV_ABI_VERSION; }
+const char *lm_bev_last_error(void) { return g_err; }
+
+int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, size_t *bytes) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!bytes || n_points < 0) return fail(LM_ERR_INVALID, "bytes is NULL or n_points < 0");
+    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
+    // the tile grid is largest with 64-row tiles: size for that so any output set fits
+    const KParams k = make_kparams(p, 6);
+    if (algo == LM_ALGO_BINNED && k.T > MAX_TILES)
+        return fail(LM_ERR_UNSUPPORTED, "%d shared-memory tiles > %d: rasterise by row windows", k.T, MAX_TILES);
+    Layout L;
+    rc = make_layout(p, n_points, algo, k.T, &L);
+    if (rc) return rc;
+    *bytes = L.total;
+    return LM_OK;
+}
+
+int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
+                     void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (n_points < 0 || (n_points > 0 && !points_dev)) return fail(LM_ERR_INVALID, "points_dev is NULL");
+    if (reinterpret_cast<uintptr_t>(points_dev) & 15) return fail(LM_ERR_INVALID, "points_dev must be 16-byte aligned");
+    if (!out || (!out->image_dev && !out->count16_dev && !out->proj_dev && !out->acc_dev))
+        return fail(LM_ERR_INVALID, "no output buffer requested");
+    if (!workspace_dev || (reinterpret_cast<uintptr_t>(workspace_dev) & 255))
+        return fail(LM_ERR_WORKSPACE, "workspace_dev is NULL or not 256-byte aligned");
+    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *w = static_cast<unsigned char *>(workspace_dev);
+    const Outs o = {out->image_dev, out->count16_dev, out->proj_dev, out->acc_dev, out->acc_band};
+    const int sms = sm_count();
+
+    if (algo == LM_ALGO_DIRECT) {
+        const KParams kp = make_kparams(p, 7);
+        Layout L;
+        rc = make_layout(p, n_points, algo, kp.T, &L);
+        if (rc) return rc;
+        // with caller-provided accumulators the workspace only carries stats
+        const size_t need = out->acc_dev ? L.off_acc : L.total;
+        if (workspace_bytes < need) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+        cudaError_t e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+        lm_bev_stats *stats = reinterpret_cast<lm_bev_stats *>(w);
+        uint32_t *acc = out->acc_dev ? out->acc_dev : reinterpret_cast<uint32_t *>(w + L.off_acc);
+        const size_t cells = (size_t)p->height * p->width;
+        acc_init_kernel<<<sms * 8, 256, 0, st>>>(acc, cells);
+        if (n_points > 0) direct_accumulate_kernel<<<sms * 8, 256, 0, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, acc, stats);
+        if (o.image || o.count16 || o.proj) {
+            Outs fo = o;
+            fo.acc = nullptr;
+            finalize_kernel<<<sms * 8, 256, 0, st>>>(kp, acc, 0, p->height, fo);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "direct path launch");
+        return LM_OK;
+    }
+
+    // ---- binned path
+    const bool want16 = out->count16_dev != nullptr;
+    const int mask = pick_mask(needed_mask(p, want16, out->acc_dev != nullptr), want16);
+    const KParams kp = make_kparams(p, tile_h_log2_for(mask));
+    if (kp.T > MAX_TILES) return fail(LM_ERR_UNSUPPORTED, "%d shared-memory tiles > %d: rasterise by row windows", kp.T, MAX_TILES);
+    Layout L;
+    rc = make_layout(p, n_points, algo, kp.T, &L);
+    if (rc) return rc;
+    if (workspace_bytes < L.total) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, L.total);
+    Ws ws;
+    ws.stats = reinterpret_cast<lm_bev_stats *>(w);
+    ws.ctl = reinterpret_cast<Ctl *>(w + L.off_ctl);
+    ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
+    ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
+    ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
+    ws.state = reinterpret_cast<uint2 *>(w + L.off_state);
+    ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
+    ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
+    ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
+    ws.acc = nullptr;
+    ws.pool_chunks = L.pool_chunks;
+
+    cudaError_t e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    if (n_points > 0) {
+        const size_t smem = bin_smem_bytes(kp.T);
+        e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
+        bin_points_kernel<<<L.bin_ctas, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+    }
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp.T);
+    if (n_points > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
+    switch (mask) {
+        case M_MAXI: e = launch_reduce<M_MAXI>(kp, ws, o, sms, st); break;
+        case M_CNT | M_MAXI: e = launch_reduce<M_CNT | M_MAXI>(kp, ws, o, sms, st); break;
+        case M_CNT | M_SUMZ | M_MAXI: e = launch_reduce<M_CNT | M_SUMZ | M_MAXI>(kp, ws, o, sms, st); break;
+        case M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ:
+            e = launch_reduce<M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ>(kp, ws, o, sms, st); break;
+        default: e = launch_reduce<M_ALL>(kp, ws, o, sms, st); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles launch");
+    return LM_OK;
+}
+
+int lm_bev_acc_merge(uint32_t *dst, int64_t dstride, const uint32_t *src, int64_t sstride, int32_t rows,
+                     int32_t width, void *stream) {
+    if (!dst || !src || rows < 0 || width <= 0) return fail(LM_ERR_INVALID, "bad acc_merge arguments");
+    if (rows == 0) return LM_OK;
+    const size_t n = (size_t)rows * width;
+    acc_merge_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, dstride, src, sstride, n);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "acc_merge launch");
+}
+
+int lm_bev_finalize(const lm_bev_params *p, const uint32_t *acc_dev, int32_t row_begin, int32_t row_end,
+                    const lm_bev_outputs *out, void *stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!acc_dev || !out) return fail(LM_ERR_INVALID, "acc_dev/out is NULL");
+    if (row_begin < 0 || row_end > p->height || row_begin > row_end) return fail(LM_ERR_INVALID, "bad row range");
+    if (row_begin == row_end) return LM_OK;
+    const KParams kp = make_kparams(p, 7);
+    const Outs o = {out->image_dev, out->count16_dev, out->proj_dev, nullptr, 0};
+    finalize_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(kp, acc_dev, row_begin, row_end, o);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "finalize launch");
+}
+
+int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, int32_t c, int32_t tile,
+                      uint8_t *crops_dev, void *stream) {
+    if (!image_dev || !crops_dev || height <= 0 || width <= 0 || c < 1 || c > 4 || tile <= 0)
+        return fail(LM_ERR_INVALID, "bad crop_tiles arguments");
+    const int ncy = (height + tile - 1) / tile, ncx = (width + tile - 1) / tile;
+    const size_t total = (size_t)ncy * ncx * tile * tile * c;
+    crop_tiles_kernel<<<sm_count() * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(image_dev, height, width, c, tile, ncx, crops_dev, total);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "crop_tiles launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/lm_bev.h declares, and
+rejects bad arguments before touching the GPU.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from lanemapping_b200 import BevSpec, _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lm_bev.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lm_bev_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(native_lib):
+    names = declared_symbols()
+    assert len(names) >= 7
+    for name in names:
+        assert hasattr(native_lib, name), f"{name} declared in lm_bev.h but not exported"
+    assert sorted(_cabi.SYMBOLS) == names, "ctypes binding and header disagree"
+    assert native_lib.lm_bev_abi_version() == _cabi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_cabi.LmBevParams) == 4 * 4 + 4 * 4 + 2 * 4 + 2 * 4 + 4 + 4 * 4   # 68 bytes, no padding
+    assert C.sizeof(_cabi.LmBevOutputs) == 4 * 8 + 8
+    assert C.sizeof(_cabi.LmBevStats) == 32 and _cabi.LmBevStats.n_valid.offset == 8
+
+
+def test_workspace_bytes_and_argument_errors(native_lib):
+    spec = BevSpec(11520, 1152)
+    p = _cabi.make_params(spec)
+    out = C.c_size_t(0)
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_BINNED, C.byref(out)) == 0
+    binned = out.value
+    assert 4e8 < binned < 4e9 and binned % 256 == 0       # N*4 B of records + chunk slack
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_DIRECT, C.byref(out)) == 0
+    assert out.value >= 6 * 4 * spec.cells
+    # errors: negative codes + a message, nothing launched
+    assert native_lib.lm_bev_workspace_bytes(None, 10, 0, C.byref(out)) == -1
+    assert b"NULL" in native_lib.lm_bev_last_error()
+    p.n_channels = 5
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 0, C.byref(out)) == -1
+    p = _cabi.make_params(spec)
+    p.inten_min = 40000
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 0, C.byref(out)) == -1
+    p = _cabi.make_params(spec)
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 7, C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), -1, 0, C.byref(out)) == -1
+    # too many shared-memory tiles for one call -> unsupported, shard by row window
+    big = _cabi.make_params(BevSpec(200_000, 200_000))
+    assert native_lib.lm_bev_workspace_bytes(C.byref(big), 10, 0, C.byref(out)) == -3
+    o = _cabi.LmBevOutputs()
+    assert native_lib.lm_bev_rasterize(C.byref(p), None, 0, 0, None, 0, C.byref(o), None) == -1  # no outputs
+    o.image_dev = 256
+    assert native_lib.lm_bev_rasterize(C.byref(p), None, 0, 0, None, 0, C.byref(o), None) == -2  # no workspace
+    assert native_lib.lm_bev_rasterize(C.byref(p), 8, 4, 0, 256, 1 << 30, C.byref(o), None) == -1  # misaligned pts
+    assert native_lib.lm_bev_crop_tiles(None, 1, 1, 3, 1152, None, None) == -1
+    assert native_lib.lm_bev_acc_merge(None, 0, None, 0, 1, 1, None) == -1
+    assert native_lib.lm_bev_finalize(C.byref(p), None, 0, 1, C.byref(o), None) == -1
+
+
+def test_product_path_has_no_cpu_fallback():
+    """The package must not import the oracle, and must refuse CPU tensors."""
+    import torch
+    from lanemapping_b200 import bev
+    pkg = os.path.join(ROOT, "lanemapping_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+    with pytest.raises(RuntimeError, match="CUDA"):
+        bev.BevRasterizer(BevSpec(8, 8), 16, device="cpu")

@@ -1,0 +1,185 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle on the same seeded
+inputs.  Bar: bit-exact on every integer output (cells, counts, sums, max/min, u8 channels,
+u16 count plane); f32 proj bit-exact too (it is a single IEEE division of a u8 by 255)."""
+import numpy as np
+import pytest
+import torch
+
+from lanemapping_b200 import (BevSpec, CH_DENSITY, CH_MAX_I, CH_MAX_Z, CH_MEAN_I, CH_MEAN_Z, CH_MIN_Z)
+from lanemapping_b200.synth import default_min_ele, make_cloud
+from oracle import bev_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CFG2_CH = (CH_MAX_I, CH_MEAN_Z, CH_DENSITY)
+CFG4_CH = (CH_MAX_I, CH_MEAN_I, CH_MIN_Z, CH_MAX_Z)
+
+
+@pytest.fixture(scope="module")
+def bev(native_lib):
+    from lanemapping_b200 import bev as B
+    assert torch.cuda.is_available()
+    return B
+
+
+def run_gpu(bev, cloud, spec, algo, outputs):
+    pts = torch.from_numpy(np.ascontiguousarray(cloud)).cuda()
+    r = bev.BevRasterizer(spec, max(1, len(cloud)), algo=algo, outputs=outputs)
+    out = r(pts)
+    torch.cuda.synchronize()
+    st = r.stats()
+    assert st["error"] == 0, st
+    return {k: v.cpu().numpy() for k, v in out.items()}, st
+
+
+def assert_matches_oracle(bev, cloud, spec, algo, with_acc=False):
+    outputs = ["image", "proj"] + (["count16"] if spec.count16 else []) + (["acc"] if with_acc else [])
+    got, st = run_gpu(bev, cloud, spec, algo, outputs)
+    acc = O.accumulate(cloud, spec)
+    want = O.finalize(acc, spec)
+    assert st["n_valid"] == int(acc[O.ACC_COUNT].sum())
+    assert np.array_equal(got["image"], want["image"]), "u8 image differs"
+    if spec.count16:
+        assert np.array_equal(got["count16"], want["count16"]), "count16 differs"
+    assert np.array_equal(got["proj"], O.proj_from_image(want["image"])), "f32 proj differs"
+    if with_acc:
+        assert np.array_equal(got["acc"].view(np.uint32), acc), "raw accumulators differ"
+    return got
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+@pytest.mark.parametrize("order", ["scan", "shuffled"])
+def test_cfg2_like_segment(bev, algo, order):
+    # 2 x 1 crops of the cfg-2 geometry, 2 M points: oracle finishes in seconds
+    spec = BevSpec(2304, 1152, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(2304, 1152)))
+    cloud = make_cloud(2_000_000, spec, order=order)
+    assert_matches_oracle(bev, cloud, spec, algo)
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+def test_cfg1_single_channel_tile(bev, algo):
+    spec = BevSpec(1152, 1152, channels=(CH_MAX_I,), local_min_ele=default_min_ele(BevSpec(1152, 1152)))
+    cloud = make_cloud(1_000_000, spec, order="scan")
+    assert_matches_oracle(bev, cloud, spec, algo)
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+@pytest.mark.parametrize("order", ["scan", "shuffled"])
+def test_cfg4_fine_resolution_five_outputs(bev, algo, order):
+    base = BevSpec(2304, 1152, img_reso=(0.02, 0.02), ele_reso=0.02, channels=CFG4_CH, count16=True)
+    spec = BevSpec(2304, 1152, img_reso=(0.02, 0.02), ele_reso=0.02, channels=CFG4_CH, count16=True,
+                   local_min_ele=default_min_ele(base))
+    cloud = make_cloud(1_500_000, spec, order=order)
+    assert_matches_oracle(bev, cloud, spec, algo)
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+def test_raw_accumulators_all_planes(bev, algo):
+    spec = BevSpec(300, 260, img_reso=(0.1, 0.1), channels=CFG2_CH, count16=True, local_min_ele=-2.0,
+                   bev_img_offset=(12.5, -3.25))
+    cloud = make_cloud(400_000, spec, seed=5, order="shuffled")
+    assert_matches_oracle(bev, cloud, spec, algo, with_acc=True)
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+@pytest.mark.parametrize("channels", [(CH_DENSITY,), (CH_MIN_Z,), (CH_MEAN_I, CH_MAX_Z), (CH_MEAN_Z, CH_MIN_Z, CH_MAX_I, CH_DENSITY),
+                                      (CH_MAX_Z, CH_MAX_Z, CH_MAX_I)])
+def test_channel_sets_on_ragged_grid(bev, algo, channels):
+    # dimensions that are not multiples of the 128/64 shared-memory tile nor of 4 bytes
+    spec = BevSpec(201, 333, img_reso=(0.07, 0.13), ele_reso=0.03, channels=channels, local_min_ele=-1.5,
+                   bev_img_offset=(-5.0, 2.0), count16=(len(channels) % 2 == 0))
+    cloud = make_cloud(300_000, spec, seed=9, order="shuffled")
+    assert_matches_oracle(bev, cloud, spec, algo)
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+def test_window_into_global_grid(bev, algo):
+    full = BevSpec(700, 500, bev_img_offset=(100.0, -40.0), channels=CFG2_CH, local_min_ele=-2.0)
+    cloud = make_cloud(500_000, full, seed=21, order="scan")
+    sub = full.window(130, 577, 64, 450)
+    got = assert_matches_oracle(bev, cloud, sub, algo)
+    whole = O.rasterize(cloud, full)["image"]
+    assert np.array_equal(got["image"], whole[130:577, 64:450])
+
+
+@pytest.mark.parametrize("algo", ["direct", "binned"])
+def test_edge_inputs(bev, algo):
+    spec = BevSpec(130, 129, img_reso=(1.0, 1.0), ele_reso=0.1, channels=CFG2_CH, count16=True)
+    # empty cloud -> all-zero raster
+    got, st = run_gpu(bev, np.zeros((0, 4), np.float32), spec, algo, ["image", "count16"])
+    assert not got["image"].any() and not got["count16"].any() and st["n_valid"] == 0
+    # every point outside / NaN -> dropped, never clamped
+    bad = np.array([[-1.0, 5, 0, 900], [5, 1e9, 0, 900], [np.nan, 5, 0, 900], [5, np.nan, 0, 900],
+                    [np.inf, 5, 0, 900], [130.0, 5, 0, 900], [5, 129.0, 0, 900]], np.float32)
+    got, st = run_gpu(bev, bad, spec, algo, ["image"])
+    assert not got["image"].any() and st["n_valid"] == 0
+    # NaN z / NaN intensity on an inside point, exact cell boundaries, negative zero
+    edge = np.array([[5.5, 5.5, np.nan, np.nan], [129.99999, 128.99999, 1.0, 1e9], [-0.0, 0.0, 0.05, 800.0],
+                     [64.0, 64.0, 0.25, 33000.0], [63.999996, 63.999996, 0.35, 32999.0]], np.float32)
+    assert_matches_oracle(bev, edge, spec, algo, with_acc=True)
+    # 300k points in ONE cell: hot-cell atomics, density and count16 saturation
+    hot = np.tile(np.array([[7.5, 9.5, 1.23, 20000.0]], np.float32), (300_000, 1))
+    hot[::3, 2] = 4.0
+    hot[1::3, 3] = 2500.0
+    got = assert_matches_oracle(bev, hot, spec, algo, with_acc=True)
+    assert got["image"][7, 9, 2] == 255 and got["count16"][7, 9] == 65535
+
+
+def test_binned_equals_direct_and_is_deterministic(bev):
+    spec = BevSpec(1152, 1152, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(1152, 1152)), count16=True)
+    cloud = make_cloud(3_000_000, spec, seed=77, order="shuffled")
+    a, _ = run_gpu(bev, cloud, spec, "binned", ["image", "count16", "acc"])
+    b, _ = run_gpu(bev, cloud, spec, "binned", ["image", "count16", "acc"])
+    d, _ = run_gpu(bev, cloud, spec, "direct", ["image", "count16", "acc"])
+    for k in a:
+        assert np.array_equal(a[k], b[k]), f"binned run-to-run difference in {k}"
+        assert np.array_equal(a[k], d[k]), f"binned != direct in {k}"
+
+
+def test_workspace_reuse_across_calls(bev):
+    spec = BevSpec(640, 384, channels=CFG2_CH, local_min_ele=-2.0)
+    r = bev.BevRasterizer(spec, 600_000, outputs=["image"])
+    for seed, n in ((1, 600_000), (2, 1234), (3, 0), (4, 450_001)):
+        cloud = make_cloud(n, spec, seed=seed, order="scan")
+        out = r(torch.from_numpy(cloud).cuda())
+        torch.cuda.synchronize()
+        r.check_device_errors()
+        assert np.array_equal(out["image"].cpu().numpy(), O.rasterize(cloud, spec)["image"])
+
+
+def test_merge_finalize_and_crops(bev):
+    spec = BevSpec(500, 300, img_reso=(0.1, 0.1), channels=CFG4_CH, count16=True, local_min_ele=-2.0)
+    cloud = make_cloud(400_000, spec, seed=13, order="shuffled")
+    half = len(cloud) // 3
+    ra = bev.BevRasterizer(spec, len(cloud), outputs=["acc"])
+    a = ra(torch.from_numpy(cloud[:half]).cuda())["acc"]
+    b = bev.BevRasterizer(spec, len(cloud), algo="direct", outputs=["acc"])(torch.from_numpy(cloud[half:]).cuda())["acc"]
+    # halo-merge law on a row band (views into the full planes), then the whole raster
+    bev.acc_merge_(a[:, 100:228], b[:, 100:228])
+    want = O.accumulate(cloud[:half], spec)
+    other = O.accumulate(cloud[half:], spec)
+    want[:, 100:228] = O.merge_acc(want[:, 100:228], other[:, 100:228])
+    torch.cuda.synchronize()
+    assert np.array_equal(a.cpu().numpy().view(np.uint32), want)
+    bev.acc_merge_(a[:, :100], b[:, :100])
+    bev.acc_merge_(a[:, 228:], b[:, 228:])
+    out = {"image": torch.zeros((500, 300, 4), dtype=torch.uint8, device="cuda"),
+           "count16": torch.zeros((500, 300), dtype=torch.uint16, device="cuda")}
+    bev.finalize_rows(spec, a, 37, 411, out)
+    full = O.rasterize(cloud, spec)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["image"].cpu().numpy()[37:411], full["image"][37:411])
+    assert np.array_equal(out["count16"].cpu().numpy()[37:411], full["count16"][37:411])
+    assert not out["image"][:37].any() and not out["image"][411:].any()
+    crops = bev.crop_tiles(torch.from_numpy(full["image"]).cuda(), tile=128)
+    assert np.array_equal(crops.cpu().numpy(), O.crop_tiles(full["image"], tile=128))
+
+
+def test_host_rasterizer_e2e(bev):
+    spec = BevSpec(1152, 1152, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(1152, 1152)))
+    cloud = make_cloud(500_000, spec, seed=3)
+    hr = bev.HostRasterizer(spec, len(cloud))
+    pinned = torch.from_numpy(cloud).pin_memory()
+    img = hr(pinned)["image"]
+    assert np.array_equal(img, O.rasterize(cloud, spec)["image"])
+    assert hr.h2d_bytes == len(cloud) * 16 and hr.d2h_bytes == spec.cells * 3

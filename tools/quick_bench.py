@@ -1,0 +1,40 @@
+"""Quick device-resident timing of lm_bev_rasterize (dev tool; bench.py is the contract)."""
+import argparse, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from lanemapping_b200.synth import make_cloud, config_spec
+from lanemapping_b200.bev import BevRasterizer
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--cfg", type=int, default=2)
+ap.add_argument("--n", type=int, default=0)
+ap.add_argument("--orders", default="scan,shuffled")
+ap.add_argument("--algos", default="binned,direct")
+ap.add_argument("--reps", type=int, default=5)
+a = ap.parse_args()
+spec, n = config_spec(a.cfg)
+n = a.n or n
+for order in a.orders.split(","):
+    t0 = time.time()
+    cloud = make_cloud(n, spec, order=order)
+    pts = torch.from_numpy(cloud).cuda()
+    print(f"cfg{a.cfg} {order}: generated {n} pts in {time.time()-t0:.1f}s", flush=True)
+    for algo in a.algos.split(","):
+        outs = ["image"] + (["count16"] if spec.count16 else [])
+        r = BevRasterizer(spec, n, algo=algo, outputs=outs)
+        out = r.alloc_outputs()
+        for _ in range(2):
+            r(pts, out=out)
+        torch.cuda.synchronize()
+        st = r.stats()
+        ts = []
+        for _ in range(a.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r(pts, out=out); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = min(ts)
+        balg = spec.algorithmic_bytes(n)
+        print(f"  {algo:7s} best {ms:8.3f} ms  median {np.median(ts):8.3f}  {n/ms/1e3:9.1f} Mpts/s  "
+              f"{balg/ms/1e6:7.1f} GB/s alg ({balg/ms/1e6/6538*100:5.1f}% of 6538)  ws={r.workspace.numel()/1e9:.2f} GB stats={st}", flush=True)
+        del r, out
+    del pts
