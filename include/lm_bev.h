@@ -130,6 +130,14 @@ int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_
                      void *workspace_dev, size_t workspace_bytes,
                      const lm_bev_outputs *out, void *stream);
 
+/* Same call, restricted to some pipeline stages (for per-kernel timing with events between
+ * the stages; running BIN, INDEX, REDUCE back to back on one stream == lm_bev_rasterize).
+ * LM_ALGO_DIRECT: BIN = init + accumulate, REDUCE = finalize, INDEX = nothing.            */
+enum { LM_STAGE_BIN = 1, LM_STAGE_INDEX = 2, LM_STAGE_REDUCE = 4, LM_STAGE_ALL = 7 };
+int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
+                            void *workspace_dev, size_t workspace_bytes,
+                            const lm_bev_outputs *out, void *stream, int stages);
+
 /* dst = merge(dst, src) over rows [0,rows) of two accumulator sets whose planes are
  * dst_plane_stride / src_plane_stride ELEMENTS apart (count, sums: add; max: max; min: min).
  * This is the halo-merge law of strip sharding.                 */

@@ -10,6 +10,7 @@ from .build import LIB_PATH
 
 ABI_VERSION = 1
 ALGO_BINNED, ALGO_DIRECT = 0, 1
+STAGE_BIN, STAGE_INDEX, STAGE_REDUCE, STAGE_ALL = 1, 2, 4, 7
 DEV_ERR_POOL, DEV_ERR_CELL_OVERFLOW = 1, 2
 
 
@@ -52,6 +53,8 @@ SYMBOLS = {
     "lm_bev_workspace_bytes": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
     "lm_bev_rasterize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
                                    C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_bev_rasterize_stages": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.POINTER(LmBevOutputs), C.c_void_p, C.c_int]),
     "lm_bev_acc_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "lm_bev_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32,
                                   C.POINTER(LmBevOutputs), C.c_void_p]),

@@ -77,7 +77,7 @@ class BevRasterizer:
 
     # -- the call ---------------------------------------------------------------------------
     def __call__(self, points: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None,
-                 stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+                 stream: Optional[torch.cuda.Stream] = None, stages: int = _cabi.STAGE_ALL) -> Dict[str, torch.Tensor]:
         """Enqueue one rasterisation of ``points`` (f32 [N,4] contiguous, on this device)."""
         if points.device != self.workspace.device and points.device.index != self.workspace.device.index:
             raise ValueError("points must live on the rasteriser's device")
@@ -96,9 +96,9 @@ class BevRasterizer:
         o.acc_band = self.acc_band
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.lm_bev_rasterize(
+            _cabi.check(self._lib.lm_bev_rasterize_stages(
                 C.byref(self._params), points.data_ptr() if n else None, n, ALGOS[self.algo],
-                self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream))
+                self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream, int(stages)))
         return out
 
     def stats(self) -> dict:

@@ -720,6 +720,13 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, s
 
 int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
                      void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream) {
+    return lm_bev_rasterize_stages(p, points_dev, n_points, algo, workspace_dev, workspace_bytes, out, stream,
+                                   LM_STAGE_ALL);
+}
+
+int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
+                            void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream,
+                            int stages) {
     int rc = validate(p);
     if (rc) return rc;
     if (n_points < 0 || (n_points > 0 && !points_dev)) return fail(LM_ERR_INVALID, "points_dev is NULL");
@@ -742,14 +749,17 @@ int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_
         // with caller-provided accumulators the workspace only carries stats
         const size_t need = out->acc_dev ? L.off_acc : L.total;
         if (workspace_bytes < need) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
-        cudaError_t e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
-        if (e != cudaSuccess) return cuda_fail(e, "memset");
+        cudaError_t e = cudaSuccess;
         lm_bev_stats *stats = reinterpret_cast<lm_bev_stats *>(w);
         uint32_t *acc = out->acc_dev ? out->acc_dev : reinterpret_cast<uint32_t *>(w + L.off_acc);
         const size_t cells = (size_t)p->height * p->width;
-        acc_init_kernel<<<sms * 8, 256, 0, st>>>(acc, cells);
-        if (n_points > 0) direct_accumulate_kernel<<<sms * 8, 256, 0, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, acc, stats);
-        if (o.image || o.count16 || o.proj) {
+        if (stages & LM_STAGE_BIN) {
+            e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
+            if (e != cudaSuccess) return cuda_fail(e, "memset");
+            acc_init_kernel<<<sms * 8, 256, 0, st>>>(acc, cells);
+            if (n_points > 0) direct_accumulate_kernel<<<sms * 8, 256, 0, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, acc, stats);
+        }
+        if ((stages & LM_STAGE_REDUCE) && (o.image || o.count16 || o.proj)) {
             Outs fo = o;
             fo.acc = nullptr;
             finalize_kernel<<<sms * 8, 256, 0, st>>>(kp, acc, 0, p->height, fo);
@@ -781,18 +791,24 @@ int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_
     ws.acc = nullptr;
     ws.pool_chunks = L.pool_chunks;
 
-    cudaError_t e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
-    if (e != cudaSuccess) return cuda_fail(e, "memset");
-    if (n_points > 0) {
-        const size_t smem = bin_smem_bytes(kp.T);
-        e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-        bin_points_kernel<<<L.bin_ctas, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+    cudaError_t e = cudaSuccess;
+    if (stages & LM_STAGE_BIN) {
+        e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+        if (n_points > 0) {
+            const size_t smem = bin_smem_bytes(kp.T);
+            e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
+            bin_points_kernel<<<L.bin_ctas, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+        }
     }
-    scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp.T);
-    if (n_points > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
+    if (stages & LM_STAGE_INDEX) {
+        scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp.T);
+        if (n_points > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
+    if (!(stages & LM_STAGE_REDUCE)) return LM_OK;
     switch (mask) {
         case M_MAXI: e = launch_reduce<M_MAXI>(kp, ws, o, sms, st); break;
         case M_CNT | M_MAXI: e = launch_reduce<M_CNT | M_MAXI>(kp, ws, o, sms, st); break;

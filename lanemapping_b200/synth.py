@@ -27,7 +27,7 @@ SEED = 2021  # reference configs/*:8
 
 
 def make_cloud(n_points: int, spec: BevSpec, seed: int = SEED, order: str = "scan",
-               chunk: int = 1 << 24, out: np.ndarray | None = None) -> np.ndarray:
+               chunk: int = 1 << 24, out: np.ndarray | None = None, roads: int | None = None) -> np.ndarray:
     """Return float32 [n_points, 4] (x, y, z, intensity) in the raster's local frame.
 
     Generated chunk by chunk (deterministic for a given (n_points, seed, order, chunk)) so
@@ -43,7 +43,10 @@ def make_cloud(n_points: int, spec: BevSpec, seed: int = SEED, order: str = "sca
     width = spec.width * spec.img_reso[1]        # cross-track extent  (cols)
     x_lo = spec.bev_img_offset[0] + spec.row0 * spec.img_reso[0]
     y_lo = spec.bev_img_offset[1] + spec.col0 * spec.img_reso[1]
-    centre = y_lo + 0.5 * width
+    # one road per 57.6 m (one 1152-px crop at 0.05 m) of cross-track extent unless told otherwise
+    if roads is None:
+        roads = max(1, int(round(width / 57.6)))
+    pitch = width / roads
     ss = np.random.SeedSequence([seed, n_points, 0 if order == "scan" else 1])
     n_chunks = max(1, -(-n_points // chunk))
     for ci, child in enumerate(ss.spawn(n_chunks)):
@@ -59,7 +62,8 @@ def make_cloud(n_points: int, spec: BevSpec, seed: int = SEED, order: str = "sca
         else:
             x = rng.random(m) * length
         x += x_lo
-        # cross-track mixture
+        # cross-track mixture (each point belongs to one of `roads` parallel roads)
+        centre = y_lo + (rng.integers(0, roads, m) + 0.5) * pitch if roads > 1 else y_lo + 0.5 * width
         y = np.where(rng.random(m) < 0.8, rng.normal(centre, 6.0, m), y_lo + rng.random(m) * width)
         # ~0.5 % thrown well outside (either axis)
         outside = rng.random(m) < 0.005
@@ -102,7 +106,7 @@ def config_spec(cfg: int) -> tuple[BevSpec, int]:
         n = 1_000_000_000
     elif cfg == 4:
         sp = BevSpec(28800, 3456, img_reso=(0.02, 0.02), ele_reso=0.02,
-                     channels=(S.CH_MAX_I, S.CH_MEAN_I, S.CH_MIN_Z, S.CH_MAX_Z), count16=True)
+                     channels=(S.CH_MAX_I, S.CH_MIN_Z, S.CH_MEAN_I, S.CH_MAX_Z), count16=True)  # index 1 = elevation
         n = 100_000_000
     elif cfg == 5:
         sp = BevSpec(1152, 1152, channels=(S.CH_MAX_I, S.CH_MEAN_Z, S.CH_DENSITY))
