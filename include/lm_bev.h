@@ -119,8 +119,11 @@ typedef struct lm_bev_stats {
 int         lm_bev_abi_version(void);
 const char *lm_bev_last_error(void);
 
-/* Bytes of device workspace lm_bev_rasterize needs for n_points points (256-B aligned). */
-int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, size_t *bytes);
+/* Bytes of device workspace lm_bev_rasterize needs for n_points points (256-B aligned).
+ * out: the output set the call will use (only which pointers are non-NULL matters: it fixes the
+ * shared-memory tile size); NULL = an upper bound valid for every output set.            */
+int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo,
+                           const lm_bev_outputs *out, size_t *bytes);
 
 /* points_dev: n_points packed records (x, y, z, intensity) of 4 x f32 = one 16-byte float4
  * each, 16-byte aligned, in the raster's local frame (the LAS read offset and the sidecar
@@ -155,6 +158,12 @@ int lm_bev_finalize(const lm_bev_params *p, const uint32_t *acc_dev,
  * tile = 1152 for cropped_tiff (reference configs/Proj_polyline_fpn_vit_vertex_2.py:38).  */
 int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, int32_t c,
                       int32_t tile, uint8_t *crops_dev, void *stream);
+
+/* Self-test of the kernels' division: they compute a / divisor (divisor = img_reso, ele_reso)
+ * with a 3-operation exact sequence instead of the generic IEEE division.  This runs that
+ * sequence against __fdiv_rn for ALL 2^32 binary32 dividends: out2_dev[0] = mismatches (must be
+ * 0), out2_dev[1] = dividends covered by the fast path (the rest take __fdiv_rn itself).     */
+int lm_bev_selftest_div(float divisor, unsigned long long *out2_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,8 @@ class LmBevStats(C.Structure):
 SYMBOLS = {
     "lm_bev_abi_version": (C.c_int, []),
     "lm_bev_last_error": (C.c_char_p, []),
-    "lm_bev_workspace_bytes": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
+    "lm_bev_workspace_bytes": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(LmBevOutputs),
+                                         C.POINTER(C.c_size_t)]),
     "lm_bev_rasterize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
                                    C.POINTER(LmBevOutputs), C.c_void_p]),
     "lm_bev_rasterize_stages": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
@@ -58,6 +59,7 @@ SYMBOLS = {
     "lm_bev_acc_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "lm_bev_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32,
                                   C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_bev_selftest_div": (C.c_int, [C.c_float, C.c_void_p, C.c_void_p]),
     "lm_bev_crop_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 

@@ -18,10 +18,18 @@ ALGOS = {"binned": _cabi.ALGO_BINNED, "direct": _cabi.ALGO_DIRECT}
 OUTPUT_KEYS = ("image", "count16", "proj", "acc")
 
 
-def workspace_bytes(spec: BevSpec, n_points: int, algo: str = "binned") -> int:
+def workspace_bytes(spec: BevSpec, n_points: int, algo: str = "binned",
+                    outputs: Optional[Iterable[str]] = None) -> int:
+    """Device workspace for one call; ``outputs`` (the buffers that will be requested) tightens it."""
     p = _cabi.make_params(spec)
     out = C.c_size_t(0)
-    _cabi.check(_cabi.lib().lm_bev_workspace_bytes(C.byref(p), int(n_points), ALGOS[algo], C.byref(out)))
+    o = None
+    if outputs is not None:
+        o = _cabi.LmBevOutputs()
+        for k in outputs:                      # only non-NULL-ness matters for sizing
+            setattr(o, k + "_dev", 1)
+    _cabi.check(_cabi.lib().lm_bev_workspace_bytes(C.byref(p), int(n_points), ALGOS[algo],
+                                                   C.byref(o) if o is not None else None, C.byref(out)))
     return int(out.value)
 
 
@@ -57,7 +65,7 @@ class BevRasterizer:
         self.max_points = int(max_points)
         self._params = _cabi.make_params(spec)
         self._lib = _cabi.lib()
-        self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo), dtype=torch.uint8,
+        self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo, outputs), dtype=torch.uint8,
                                      device=self.device)
 
     # -- buffers ----------------------------------------------------------------------------

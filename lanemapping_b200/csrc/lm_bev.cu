@@ -40,6 +40,7 @@ constexpr int BIN_PPT = 8;                // points per thread per batch
 constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
 constexpr int MAX_BIN_CTAS = 148 * 4;     // sizing constant of the workspace (B200: 148 SMs)
 constexpr int RED_THREADS = 512;
+constexpr int RED_MIN_CTAS = 2;          // shared-memory tiles are sized so that two CTAs fit per SM
 constexpr int MAX_TILES = 40000;          // limit of bin_points' shared-memory histogram
 constexpr uint32_t INVALID_U32 = 0xFFFFFFFFu;
 
@@ -56,9 +57,11 @@ struct KParams {
     int H, W, row0, col0;
     float off0, off1, reso0, reso1, zmin, zreso;
     float row_lo, row_hi, col_lo, col_hi;
+    float rreso0, rreso1, rzreso;   // RN(1/reso): operands of the exact 3-op division
+    int fast_div;                   // all three divisors in the range div_const is proven for
     float imin_f, imax_f;
     int imin;
-    unsigned long long imagic;  // floor(2^40 / (imax-imin)) + 1: exact n/d for n < 2^24
+    uint32_t imagic, ishift;        // n/d == umulhi(n << 8, imagic) >> ishift for n < 2^24
     int nch;
     int ch[4];
     int tile_h_log2, tiles_x, tiles_y, T;
@@ -76,9 +79,10 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t *tile_nchunks;  // [T]
     uint32_t *tile_first;    // [T]
     uint32_t *tile_cursor;   // [T]
+    uint32_t *tile_order;    // [T] tiles sorted heaviest first (reduce_tiles schedule)
     uint2 *state;            // [MAX_BIN_CTAS][T] {cur chunk id, fill}
     uint2 *chunk_meta;       // [P] {tile, count}
-    uint32_t *chunk_index;   // [P]
+    uint32_t *chunk_index;   // [P] per-tile chunk lists: id | (count-1) << 23
     uint32_t *pool;          // [P][CHUNK_RECS]
     uint32_t *acc;           // direct path: [6][H][W]
     uint32_t pool_chunks;    // P
@@ -109,22 +113,46 @@ int cuda_fail(cudaError_t e, const char *what) {
 // ------------------------------------------------------------------------------------------
 // per-point quantisation (the spec; oracle/bev_oracle.py::quantise_points restates it)
 // ------------------------------------------------------------------------------------------
+// a / c for a loop-invariant divisor, bit-identical to __fdiv_rn(a, c).
+// Markstein's theorem: with rc = RN(1/c), q0 = RN(a*rc) is a faithful quotient, r = a - q0*c is
+// exact in one FMA, and RN(q0 + r*rc) is the correctly rounded a/c -- provided nothing over- or
+// underflows, which the exponent guard ensures (callers take the __fdiv_rn path otherwise).
+// tests/test_gpu_parity.py::test_exact_division_exhaustive compares all 2^32 dividends.
+__device__ __forceinline__ float div_const(float a, float c, float rc) {
+    const float q0 = __fmul_rn(a, rc);
+    const float r = __fmaf_rn(-q0, c, a);
+    return __fmaf_rn(r, rc, q0);
+}
+// dividend exponent in [2^-40, 2^64): the range div_const is used for (0, tiny, huge, inf, nan -> slow path)
+__device__ __forceinline__ bool div_fast_ok(float a) {
+    return ((__float_as_uint(a) >> 23) & 0xFFu) - 87u < 104u;
+}
+
 __device__ __forceinline__ bool quantise(const float4 p, const KParams &k, int &lrow, int &lcol,
                                          uint32_t &iq, uint32_t &zq) {
     // inverse of reference baseline/utils/coor_img2pc.py:136-139 (row <-> x, col <-> y)
-    const float rf = floorf(__fdiv_rn(__fsub_rn(p.x, k.off0), k.reso0));
-    const float cf = floorf(__fdiv_rn(__fsub_rn(p.y, k.off1), k.reso1));
+    const float dx = __fsub_rn(p.x, k.off0), dy = __fsub_rn(p.y, k.off1), dz = __fsub_rn(p.z, k.zmin);
+    float qx, qy, qz;
+    if (k.fast_div && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz)) {
+        qx = div_const(dx, k.reso0, k.rreso0);
+        qy = div_const(dy, k.reso1, k.rreso1);
+        qz = div_const(dz, k.zreso, k.rzreso);
+    } else {
+        qx = __fdiv_rn(dx, k.reso0);
+        qy = __fdiv_rn(dy, k.reso1);
+        qz = __fdiv_rn(dz, k.zreso);
+    }
+    const float rf = floorf(qx), cf = floorf(qy);
     const bool valid = (rf >= k.row_lo) && (rf < k.row_hi) && (cf >= k.col_lo) && (cf < k.col_hi);  // NaN -> false
     lrow = (int)rf - k.row0;
     lcol = (int)cf - k.col0;
     // inverse of coor_img2pc.py:150, round-half-even; NaN -> 0 through fmaxf
-    float zf = rintf(__fdiv_rn(__fsub_rn(p.z, k.zmin), k.zreso));
-    zf = fminf(fmaxf(zf, 0.0f), 255.0f);
+    const float zf = fminf(fmaxf(rintf(qz), 0.0f), 255.0f);
     zq = (uint32_t)(int)zf;
     // clip of reference baseline/datasets/laserlane_proposals.py:626-628, then u8 mapping
     const float ic = fminf(fmaxf(p.w, k.imin_f), k.imax_f);
-    const uint32_t n = (uint32_t)((int)ic - k.imin) * 255u;      // < 2^24
-    iq = (uint32_t)(((unsigned long long)n * k.imagic) >> 40);    // == n / (imax-imin)
+    const uint32_t n = (uint32_t)((int)ic - k.imin) * 65280u;     // ((I-imin)*255) << 8, < 2^32
+    iq = __umulhi(n, k.imagic) >> k.ishift;                        // == (I-imin)*255 / (imax-imin)
     return valid;
 }
 
@@ -230,7 +258,7 @@ __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_
     atomicAdd(&ws.tile_nchunks[tile], 1u);
 }
 
-__global__ void __launch_bounds__(BIN_THREADS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
+__global__ void __launch_bounds__(BIN_THREADS, 4) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
                                                                  long long n, Ws ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = kp.T;
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_points_kernel(KParams kp, con
             }
             __stcg(&my_state[t], make_uint2(cur, fill));
             desc[k] = make_uint4(start, dst0, room, dst1);
-            hist[t] = (uint32_t)k;           // tile -> descriptor index for the scatter below
+            hist[t] = ((uint32_t)k << 16) | start;   // tile -> {descriptor index, run start} for the scatter
         }
         if (tid == 0) { s_cnt[par ^ 1][0] = 0; s_cnt[par ^ 1][1] = 0; }
         __syncthreads();
@@ -315,8 +343,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_points_kernel(KParams kp, con
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
-                const uint32_t k = hist[tl[j]];
-                sorted[desc[k].x + rk[j]] = make_uint2(rec[j], k);
+                const uint32_t h = hist[tl[j]];
+                sorted[(h & 0xFFFFu) + rk[j]] = make_uint2(rec[j], h >> 16);
             }
         }
         __syncthreads();
@@ -346,6 +374,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_points_kernel(KParams kp, con
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, int T) {
     __shared__ uint32_t s_part[1024];
+    __shared__ uint32_t s_lvl[1024];
     __shared__ uint32_t s_err;
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -354,6 +383,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, int T) {
         ws.stats->n_chunks = used < ws.pool_chunks ? used : ws.pool_chunks;
         ws.stats->n_tiles = (uint32_t)T;
     }
+    s_lvl[tid] = 0;
     __syncthreads();
     const int per = (T + 1023) / 1024;
     const int lo = tid * per, hi = min(T, lo + per);
@@ -361,13 +391,19 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, int T) {
         for (int t = lo; t < hi; ++t) ws.tile_nchunks[t] = 0;
     }
     uint32_t sum = 0;
-    for (int t = lo; t < hi; ++t) sum += ws.tile_nchunks[t];
+    for (int t = lo; t < hi; ++t) {
+        const uint32_t c = ws.tile_nchunks[t];
+        sum += c;
+        atomicAdd(&s_lvl[1023u - min(c, 1023u)], 1u);      // level 0 = heaviest
+    }
     s_part[tid] = sum;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan
+    for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scans (chunk offsets, level offsets)
         const uint32_t v = tid >= o ? s_part[tid - o] : 0u;
+        const uint32_t w = tid >= o ? s_lvl[tid - o] : 0u;
         __syncthreads();
         s_part[tid] += v;
+        s_lvl[tid] += w;
         __syncthreads();
     }
     uint32_t run = s_part[tid] - sum;
@@ -375,15 +411,22 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, int T) {
         ws.tile_first[t] = run;
         run += ws.tile_nchunks[t];
     }
+    // counting sort by weight level: tile_order lists the heaviest tiles first so that the persistent
+    // reduce CTAs finish together (longest-processing-time-first)
+    for (int t = lo; t < hi; ++t) {
+        const uint32_t lvl = 1023u - min(ws.tile_nchunks[t], 1023u);
+        const uint32_t pos = atomicAdd(&s_lvl[lvl], 0xFFFFFFFFu) - 1u;      // fill each level's slot range from its end
+        ws.tile_order[pos] = (uint32_t)t;
+    }
 }
 
 __global__ void index_chunks_kernel(Ws ws) {
     if (ws.stats->error & LM_DEV_ERR_POOL) return;
     const uint32_t used = ws.ctl->pool_cursor;    // ids 1..used
     for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= used; id += gridDim.x * blockDim.x) {
-        const uint32_t t = ws.chunk_meta[id].x;
-        const uint32_t slot = ws.tile_first[t] + atomicAdd(&ws.tile_cursor[t], 1u);
-        ws.chunk_index[slot] = id;
+        const uint2 m = ws.chunk_meta[id];
+        const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], 1u);
+        ws.chunk_index[slot] = id | ((m.y - 1u) << 23);
     }
 }
 
@@ -429,7 +472,19 @@ __device__ __forceinline__ void write_image_rows(const uint32_t *__restrict__ pa
 }
 
 template <int MASK>
-__global__ void __launch_bounds__(RED_THREADS, 1) reduce_tiles_kernel(KParams kp, Ws ws, Outs out) {
+__device__ __forceinline__ void accumulate_rec(uint32_t rec, uint32_t *a_cnt, uint32_t *a_sumi, uint32_t *a_sumz,
+                                               uint32_t *a_maxi, uint32_t *a_minz, uint32_t *a_maxz) {
+    const uint32_t cell = rec >> 16, iq = (rec >> 8) & 0xFFu, zq = rec & 0xFFu;
+    if (MASK & M_CNT) atomicAdd(&a_cnt[cell], 1u);
+    if (MASK & M_SUMI) atomicAdd(&a_sumi[cell], iq);
+    if (MASK & M_SUMZ) atomicAdd(&a_sumz[cell], zq);
+    if (MASK & M_MAXI) atomicMax(&a_maxi[cell], iq);
+    if (MASK & M_MINZ) atomicMax(&a_minz[cell], 256u - zq);
+    if (MASK & M_MAXZ) atomicMax(&a_maxz[cell], zq);
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel(KParams kp, Ws ws, Outs out) {
     constexpr int NW = popc6(MASK);
     extern __shared__ __align__(16) uint32_t acc[];      // [NW][cells]; plane 0/1 reused as packed/count16
     __shared__ int s_tile;
@@ -444,20 +499,34 @@ __global__ void __launch_bounds__(RED_THREADS, 1) reduce_tiles_kernel(KParams kp
     uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
     uint32_t *packed = acc;                                      // plane 0 after the finish step
     uint32_t *cnt16 = acc + cells;                               // plane 1 after the finish step (NW >= 2)
+    constexpr int V = CHUNK_RECS / 128;                          // uint4 loads per lane per chunk
+    constexpr int NWARPS = RED_THREADS / 32;
 
     for (;;) {
         __syncthreads();
         if (tid == 0) s_tile = (int)atomicAdd(&ws.ctl->tile_counter, 1u);
         __syncthreads();
-        const int t = s_tile;
-        if (t >= kp.T) break;
+        if (s_tile >= kp.T) break;
+        const int t = (int)ws.tile_order[s_tile];               // heaviest tiles first
         const int trow = t / kp.tiles_x, tcol = t - trow * kp.tiles_x;
         const int grow0 = trow << kp.tile_h_log2, gcol0 = tcol << TILE_W_LOG2;
         const int nrows = min(TH, kp.H - grow0), ncols = min(TILE_W, kp.W - gcol0);
         const uint32_t nchunks = ws.tile_nchunks[t];
-        const uint32_t first = ws.tile_first[t];
+        const uint32_t *my_index = ws.chunk_index + ws.tile_first[t];
         const bool want_raw = out.acc != nullptr &&
                               (out.acc_band <= 0 || grow0 < out.acc_band || grow0 + nrows > kp.H - out.acc_band);
+
+        // first chunk of this warp: issue its loads before zeroing so the latency overlaps
+        uint32_t c = warp;
+        uint32_t ent = c < nchunks ? __ldg(my_index + c) : 0u;
+        uint4 v[V];
+        if (c < nchunks) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)(ent & 0x7FFFFFu) * CHUNK_RECS);
+            const uint32_t cnt = (ent >> 23) + 1u;
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                if ((uint32_t)((q * 32 + lane) * 4) < cnt) v[q] = __ldcs(src + q * 32 + lane);
+        }
 
         // ---- zero the accumulator tile
         {
@@ -467,32 +536,38 @@ __global__ void __launch_bounds__(RED_THREADS, 1) reduce_tiles_kernel(KParams kp
         }
         __syncthreads();
 
-        // ---- stream the tile's chunks: one chunk per warp, integer atomics in shared memory
-        for (uint32_t c = warp; c < nchunks; c += RED_THREADS / 32) {
-            const uint32_t id = ws.chunk_index[first + c];
-            const uint32_t cnt = ws.chunk_meta[id].y;
-            const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)id * CHUNK_RECS);
-            constexpr int V = CHUNK_RECS / 128;      // uint4 loads per lane per chunk
-            uint4 v[V];
+        // ---- stream the tile's chunks: one chunk per warp, integer atomics in shared memory;
+        //      the next chunk's index entry is fetched while the current one is reduced
+        while (c < nchunks) {
+            const uint32_t cnt = (ent >> 23) + 1u;
+            const uint32_t cn = c + NWARPS;
+            const uint32_t ent_next = cn < nchunks ? __ldg(my_index + cn) : 0u;
+            if (cnt == CHUNK_RECS) {                 // full chunk: no per-record bounds checks
 #pragma unroll
-            for (int q = 0; q < V; ++q)
-                v[q] = (uint32_t)((q * 32 + lane) * 4) < cnt ? __ldcs(src + q * 32 + lane) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int q = 0; q < V; ++q) {
-                const uint32_t r4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if ((uint32_t)((q * 32 + lane) * 4 + e) < cnt) {
-                        const uint32_t rec = r4[e];
-                        const uint32_t cell = rec >> 16, iq = (rec >> 8) & 0xFFu, zq = rec & 0xFFu;
-                        if (MASK & M_CNT) atomicAdd(&a_cnt[cell], 1u);
-                        if (MASK & M_SUMI) atomicAdd(&a_sumi[cell], iq);
-                        if (MASK & M_SUMZ) atomicAdd(&a_sumz[cell], zq);
-                        if (MASK & M_MAXI) atomicMax(&a_maxi[cell], iq);
-                        if (MASK & M_MINZ) atomicMax(&a_minz[cell], 256u - zq);
-                        if (MASK & M_MAXZ) atomicMax(&a_maxz[cell], zq);
-                    }
+                for (int q = 0; q < V; ++q) {
+                    accumulate_rec<MASK>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                    accumulate_rec<MASK>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                    accumulate_rec<MASK>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                    accumulate_rec<MASK>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
                 }
+            } else {
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    const uint32_t i0 = (uint32_t)((q * 32 + lane) * 4);
+                    if (i0 + 0 < cnt) accumulate_rec<MASK>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                    if (i0 + 1 < cnt) accumulate_rec<MASK>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                    if (i0 + 2 < cnt) accumulate_rec<MASK>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                    if (i0 + 3 < cnt) accumulate_rec<MASK>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                }
+            }
+            c = cn;
+            ent = ent_next;
+            if (c < nchunks) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)(ent & 0x7FFFFFu) * CHUNK_RECS);
+                const uint32_t cnt2 = (ent >> 23) + 1u;
+#pragma unroll
+                for (int q = 0; q < V; ++q)
+                    if ((uint32_t)((q * 32 + lane) * 4) < cnt2) v[q] = __ldcs(src + q * 32 + lane);
             }
         }
         __syncthreads();
@@ -555,6 +630,29 @@ __global__ void __launch_bounds__(RED_THREADS, 1) reduce_tiles_kernel(KParams kp
 }
 
 // ------------------------------------------------------------------------------------------
+// self-test: div_const == __fdiv_rn for EVERY binary32 dividend the fast path accepts
+// ------------------------------------------------------------------------------------------
+__global__ void selftest_div_kernel(float c, float rc, unsigned long long *out) {
+    unsigned long long bad = 0, fast = 0;
+    const unsigned long long total = 1ull << 32;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float((uint32_t)i);
+        if (!div_fast_ok(a)) continue;
+        ++fast;
+        if (__float_as_uint(div_const(a, c, rc)) != __float_as_uint(__fdiv_rn(a, c))) ++bad;
+    }
+    for (int o = 16; o; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        fast += __shfl_xor_sync(0xffffffffu, fast, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&out[0], bad);
+        atomicAdd(&out[1], fast);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -584,7 +682,9 @@ int pick_mask(int need, bool count16) {
         if ((m & need) == need && !(count16 && popc6(m) < 2)) return m;
     return M_ALL;
 }
-int tile_h_log2_for(int mask) { return popc6(mask) <= 3 ? 7 : 6; }
+// tile height so that NW planes of 128 x TH u32 stay <= 96 KB: two reduce CTAs per SM overlap
+// one tile's zero/finish/write phases with the other's streaming phase
+int tile_h_log2_for(int mask) { const int nw = popc6(mask); return nw <= 1 ? 7 : (nw <= 3 ? 6 : 5); }
 
 int validate(const lm_bev_params *p) {
     if (!p) return fail(LM_ERR_INVALID, "params is NULL");
@@ -612,8 +712,16 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     k.row_lo = (float)p->row0; k.row_hi = (float)(p->row0 + p->height);
     k.col_lo = (float)p->col0; k.col_hi = (float)(p->col0 + p->width);
     k.imin_f = (float)p->inten_min; k.imax_f = (float)p->inten_max; k.imin = p->inten_min;
+    // exact n/d for n < 2^24 (Granlund-Montgomery): l = ceil(log2 d), m = ceil(2^(24+l)/d) < 2^25,
+    // n/d = floor(n*m / 2^(24+l)) = umulhi(n << 8, m) >> l
     const unsigned long long d = (unsigned long long)(p->inten_max - p->inten_min);
-    k.imagic = d == 1 ? (1ull << 40) : ((1ull << 40) / d + 1ull);
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    k.ishift = l;
+    k.imagic = (uint32_t)(((1ull << (24 + l)) + d - 1) / d);
+    k.rreso0 = 1.0f / k.reso0; k.rreso1 = 1.0f / k.reso1; k.rzreso = 1.0f / k.zreso;
+    auto in_range = [](float c) { return c >= 0x1p-20f && c <= 0x1p20f; };
+    k.fast_div = in_range(k.reso0) && in_range(k.reso1) && in_range(k.zreso);
     k.nch = p->n_channels;
     for (int c = 0; c < 4; ++c) k.ch[c] = c < p->n_channels ? p->channels[c] : 0;
     k.tile_h_log2 = tile_h_log2;
@@ -624,7 +732,7 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
 }
 
 struct Layout {
-    size_t off_ctl, off_nchunks, off_first, off_cursor, off_state, zero_bytes;
+    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, off_state, zero_bytes;
     size_t off_meta, off_index, off_pool, off_acc, total;
     uint32_t pool_chunks;
     int bin_ctas;
@@ -653,12 +761,13 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_nchunks = o; o = align_up(o + (size_t)T * 4, 256);
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
+    L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_state = o;   o = align_up(o + (size_t)L->bin_ctas * T * sizeof(uint2), 256);
     L->zero_bytes = o;
     const unsigned long long chunks = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS) +
                                       (unsigned long long)L->bin_ctas * T + 2ull;
-    if (chunks * CHUNK_RECS >= (1ull << 32))
-        return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^32 records: shard the call (fewer points or a smaller row window)");
+    if (chunks >= (1ull << 23))     // chunk ids are 23-bit (index entries), record indices 32-bit
+        return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^23 chunks: shard the call (fewer points or a smaller row window)");
     L->pool_chunks = (uint32_t)chunks;
     L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
     L->off_index = o; o = align_up(o + (size_t)chunks * 4, 256);
@@ -702,13 +811,20 @@ extern "C" {
 int lm_bev_abi_version(void) { return LM_BEV_ABI_VERSION; }
 const char *lm_bev_last_error(void) { return g_err; }
 
-int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, size_t *bytes) {
+int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, const lm_bev_outputs *out,
+                           size_t *bytes) {
     int rc = validate(p);
     if (rc) return rc;
     if (!bytes || n_points < 0) return fail(LM_ERR_INVALID, "bytes is NULL or n_points < 0");
     if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
-    // the tile grid is largest with 64-row tiles: size for that so any output set fits
-    const KParams k = make_kparams(p, 6);
+    // the tile height depends on the accumulator planes the outputs need; without an output set
+    // size for the smallest tiles (raw accumulators) so that any call fits
+    int th = 5;
+    if (out) {
+        const bool want16 = out->count16_dev != nullptr;
+        th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr), want16));
+    }
+    const KParams k = make_kparams(p, th);
     if (algo == LM_ALGO_BINNED && k.T > MAX_TILES)
         return fail(LM_ERR_UNSUPPORTED, "%d shared-memory tiles > %d: rasterise by row windows", k.T, MAX_TILES);
     Layout L;
@@ -784,6 +900,7 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
     ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
     ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
     ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
+    ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
     ws.state = reinterpret_cast<uint2 *>(w + L.off_state);
     ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
     ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
@@ -854,6 +971,17 @@ int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, i
     crop_tiles_kernel<<<sm_count() * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(image_dev, height, width, c, tile, ncx, crops_dev, total);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? LM_OK : cuda_fail(e, "crop_tiles launch");
+}
+
+int lm_bev_selftest_div(float divisor, unsigned long long *out2_dev, void *stream) {
+    if (!out2_dev || !(divisor >= 0x1p-20f && divisor <= 0x1p20f))
+        return fail(LM_ERR_INVALID, "selftest_div: NULL output or divisor outside the fast-division range");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(out2_dev, 0, 16, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    selftest_div_kernel<<<sm_count() * 16, 256, 0, st>>>(divisor, 1.0f / divisor, out2_dev);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "selftest_div launch");
 }
 
 }  // extern "C"

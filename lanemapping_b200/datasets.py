@@ -1,0 +1,116 @@
+"""DATASETS plug-in: feed per-crop point records instead of pre-baked PNGs.
+
+The reference's loaders read ``cropped_tiff/<stem>.png`` in forked DataLoader workers
+(reference baseline/datasets/laserlane_proposals.py:73-98; ``workers=12, pin_memory=True``,
+reference baseline/datasets/registry.py:54-59).  CUDA cannot be used there, so the on-the-fly
+path splits the work: this dataset only *loads* each crop's packed point records
+(``<data_root>/crop_points/<stem>.npy`` float32 [N,4] + the sidecar) in the worker, and the
+rasterisation runs in the main process on the GPU inside the PCENCODER wrapper
+(lanemapping_b200/pcencoder.py), which fills ``sample['proj']``.
+
+Plug-in surface (reference baseline/datasets/registry.py:15-25, utils/registry.py:54-80):
+``@DATASETS.register_module class X(Dataset): __init__(self, data_root, data_split_file, mode, cfg=None)``.
+``make_onthefly_dataset(base)`` derives that class from the reference's ``LaserLaneProposal`` when
+it is importable (labels then come from its ``format_gt_column_proposal``); standalone it yields
+points + names only (inference).
+"""
+from __future__ import annotations
+
+import json
+import os
+import os.path as osp
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .sidecar import read_sidecar
+
+SPLIT_KEYS = {"train": "train", "test": "test", "valid": "valid", "single": "single", "all": "pretrain",
+              "infer_only": "pretrain"}      # reference laserlane_proposals.py:500-520
+
+
+def read_split(data_root: str, data_split_file: str, mode: str) -> List[str]:
+    with open(osp.join(data_root, data_split_file), "r") as jf:
+        js = json.load(jf)
+    if mode not in SPLIT_KEYS:
+        raise AssertionError(f"mode {mode!r} not in {sorted(SPLIT_KEYS)}")     # reference :39 asserts too
+    stems = list(js[SPLIT_KEYS[mode]])
+    if mode == "valid":
+        stems = stems[:150]                                                     # reference :512
+    return stems
+
+
+class CropPoints(Dataset):
+    """Standalone on-the-fly dataset: ``sample = {'image_name', 'points', 'bev_geom'}``."""
+
+    def __init__(self, data_root: str, data_split_file: str, mode: str, cfg=None,
+                 points_dir: str = "crop_points", param_dir: str = "cropped_tiff_param"):
+        self.data_root, self.mode, self.cfg = data_root, mode, cfg
+        self.points_path = osp.join(data_root, points_dir)
+        self.param_path = osp.join(data_root, param_dir)
+        self.image_stem_list = read_split(data_root, data_split_file, mode)
+
+    def __len__(self):
+        return len(self.image_stem_list)
+
+    def load_points(self, idx: int) -> Dict[str, torch.Tensor]:
+        stem = self.image_stem_list[idx]
+        pts = np.load(osp.join(self.points_path, stem + ".npy"))
+        if pts.ndim != 2 or pts.shape[1] != 4:
+            raise ValueError(f"{stem}.npy: expected [N,4] (x, y, z, intensity)")
+        p = read_sidecar(osp.join(self.param_path, stem + ".txt"))
+        geom = torch.tensor([p.bev_img_offset[0], p.bev_img_offset[1], p.img_reso[0], p.img_reso[1],
+                             p.local_min_ele, p.ele_reso], dtype=torch.float64)
+        return {"points": torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float32)), "bev_geom": geom}
+
+    def __getitem__(self, idx):
+        sample = dict()
+        sample["image_name"] = self.image_stem_list[idx][0:11]                 # reference :76
+        sample.update(self.load_points(idx))
+        return sample
+
+
+def make_onthefly_dataset(base, points_dir: str = "crop_points", param_dir: str = "cropped_tiff_param"):
+    """Class factory: subclass a reference dataset (e.g. LaserLaneProposal) so that it returns
+    ``points`` instead of ``proj``; label tensors still come from the base class."""
+
+    class LaserLaneProposalOnTheFly(base):          # noqa: D401 - name is what configs refer to
+        def __init__(self, data_root, data_split_file, mode, cfg=None):
+            super().__init__(data_root, data_split_file, mode, cfg=cfg)
+            self._pts = CropPoints.__new__(CropPoints)
+            self._pts.points_path = osp.join(data_root, points_dir)
+            self._pts.param_path = osp.join(data_root, param_dir)
+            self._pts.image_stem_list = self.image_stem_list
+
+        def __getitem__(self, idx):
+            sample = dict()
+            sample["image_name"] = self.image_stem_list[idx][0:11]
+            sample.update(self._pts.load_points(idx))
+            if self.mode in {"train", "valid", "test", "single", "all"}:        # reference :79-81
+                sample.update(self.format_gt_column_proposal(idx))
+            return sample
+
+    return LaserLaneProposalOnTheFly
+
+
+def collate_points(batch: List[dict]) -> dict:
+    """Collate for variable-length clouds: ``points`` stays a list of tensors (what the reference
+    anticipates with ``pseudo_collate``, reference baseline/datasets/registry.py:58, and what
+    ``Runner.to_cuda`` handles in its list branch, reference baseline/engine/runner.py:139-147);
+    everything else is default-collated."""
+    from torch.utils.data import default_collate
+    pts = [b["points"] for b in batch]
+    rest = [{k: v for k, v in b.items() if k != "points"} for b in batch]
+    out = default_collate(rest)
+    out["points"] = pts
+    return out
+
+
+def register(DATASETS, base=None):
+    """Register the on-the-fly dataset in the reference's DATASETS registry."""
+    cls = make_onthefly_dataset(base) if base is not None else CropPoints
+    if base is None:
+        cls = type("LaserLaneProposalOnTheFly", (CropPoints,), {})
+    return DATASETS.register_module(cls)

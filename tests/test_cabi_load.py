@@ -36,25 +36,29 @@ def test_workspace_bytes_and_argument_errors(native_lib):
     spec = BevSpec(11520, 1152)
     p = _cabi.make_params(spec)
     out = C.c_size_t(0)
-    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_BINNED, C.byref(out)) == 0
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_BINNED, None, C.byref(out)) == 0
     binned = out.value
-    assert 4e8 < binned < 4e9 and binned % 256 == 0       # N*4 B of records + chunk slack
-    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_DIRECT, C.byref(out)) == 0
+    assert 4e8 < binned < 8e9 and binned % 256 == 0       # N*4 B of records + chunk slack (upper bound)
+    o = _cabi.LmBevOutputs()
+    o.image_dev = 1
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_BINNED, C.byref(o), C.byref(out)) == 0
+    assert 4e8 < out.value < binned                       # the real output set needs fewer tiles
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_DIRECT, None, C.byref(out)) == 0
     assert out.value >= 6 * 4 * spec.cells
     # errors: negative codes + a message, nothing launched
-    assert native_lib.lm_bev_workspace_bytes(None, 10, 0, C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes(None, 10, 0, None, C.byref(out)) == -1
     assert b"NULL" in native_lib.lm_bev_last_error()
     p.n_channels = 5
-    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 0, C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 0, None, C.byref(out)) == -1
     p = _cabi.make_params(spec)
     p.inten_min = 40000
-    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 0, C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 0, None, C.byref(out)) == -1
     p = _cabi.make_params(spec)
-    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 7, C.byref(out)) == -1
-    assert native_lib.lm_bev_workspace_bytes(C.byref(p), -1, 0, C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 7, None, C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), -1, 0, None, C.byref(out)) == -1
     # too many shared-memory tiles for one call -> unsupported, shard by row window
     big = _cabi.make_params(BevSpec(200_000, 200_000))
-    assert native_lib.lm_bev_workspace_bytes(C.byref(big), 10, 0, C.byref(out)) == -3
+    assert native_lib.lm_bev_workspace_bytes(C.byref(big), 10, 0, None, C.byref(out)) == -3
     o = _cabi.LmBevOutputs()
     assert native_lib.lm_bev_rasterize(C.byref(p), None, 0, 0, None, 0, C.byref(o), None) == -1  # no outputs
     o.image_dev = 256

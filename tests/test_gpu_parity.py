@@ -183,3 +183,20 @@ def test_host_rasterizer_e2e(bev):
     img = hr(pinned)["image"]
     assert np.array_equal(img, O.rasterize(cloud, spec)["image"])
     assert hr.h2d_bytes == len(cloud) * 16 and hr.d2h_bytes == spec.cells * 3
+
+
+@pytest.mark.parametrize("divisor", [0.05, 0.02, 0.1, 0.07, 0.13, 0.03, 1.0, 0.25, 0.5, 1.0 / 3.0, 0.001, 1000.0,
+                                     0.0499999, 1.9999999, 3.0e-6, 7.0e5])
+def test_exact_division_exhaustive(bev, native_lib, divisor):
+    """The kernels divide by img_reso / ele_reso with a 3-operation sequence (FMUL, FFMA, FFMA).
+    It must be bit-identical to the IEEE division the spec (and the numpy oracle) uses: compare
+    against __fdiv_rn for every one of the 2^32 binary32 dividends."""
+    import ctypes as C
+    from lanemapping_b200 import _cabi
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _cabi.check(native_lib.lm_bev_selftest_div(C.c_float(divisor), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    bad, fast = (int(v) for v in out.cpu())
+    assert fast == 104 * 2**24          # dividends with exponent in [2^-40, 2^64), both signs
+    assert bad == 0, f"{bad} dividends where the fast division differs from __fdiv_rn for divisor {divisor}"

@@ -84,11 +84,17 @@ def test_window_is_a_bit_exact_subwindow():
 
 
 def test_intensity_magic_division_is_exact():
-    # the CUDA kernel replaces n // d by (n * magic) >> 40 with magic = 2^40 // d + 1 (n < 2^24)
-    for d in (1, 2, 3, 255, 32200, 65535, 12345):
-        magic = (1 << 40) if d == 1 else (1 << 40) // d + 1
+    # the CUDA kernel replaces n // d by umulhi(n << 8, m) >> l, l = ceil(log2 d), m = ceil(2^(24+l) / d)
+    for d in (1, 2, 3, 255, 256, 32200, 65535, 12345, 32768, 32769):
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        m = ((1 << (24 + l)) + d - 1) // d
+        assert m < 2**32
         n = np.arange(0, d + 1, dtype=np.uint64) * np.uint64(255)
-        assert np.array_equal((n * np.uint64(magic)) >> np.uint64(40), n // np.uint64(d))
+        assert int(n.max()) < 2**24
+        got = ((n << np.uint64(8)) * np.uint64(m) >> np.uint64(32)) >> np.uint64(l)
+        assert np.array_equal(got, n // np.uint64(d))
 
 
 @settings(max_examples=25, deadline=None)
