@@ -25,6 +25,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -123,25 +124,12 @@ __device__ __forceinline__ float div_const(float a, float c, float rc) {
     const float r = __fmaf_rn(-q0, c, a);
     return __fmaf_rn(r, rc, q0);
 }
-// dividend exponent in [2^-40, 2^64): the range div_const is used for (0, tiny, huge, inf, nan -> slow path)
-__device__ __forceinline__ bool div_fast_ok(float a) {
-    return ((__float_as_uint(a) >> 23) & 0xFFu) - 87u < 104u;
-}
+// the dividends the fast path accepts: finite magnitudes in [2^-40, 2^64)
+__device__ __forceinline__ bool div_fast_ok(float a) { return fabsf(a) >= 0x1p-40f && fabsf(a) < 0x1p64f; }
 
-__device__ __forceinline__ bool quantise(const float4 p, const KParams &k, int &lrow, int &lcol,
-                                         uint32_t &iq, uint32_t &zq) {
-    // inverse of reference baseline/utils/coor_img2pc.py:136-139 (row <-> x, col <-> y)
-    const float dx = __fsub_rn(p.x, k.off0), dy = __fsub_rn(p.y, k.off1), dz = __fsub_rn(p.z, k.zmin);
-    float qx, qy, qz;
-    if (k.fast_div && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz)) {
-        qx = div_const(dx, k.reso0, k.rreso0);
-        qy = div_const(dy, k.reso1, k.rreso1);
-        qz = div_const(dz, k.zreso, k.rzreso);
-    } else {
-        qx = __fdiv_rn(dx, k.reso0);
-        qy = __fdiv_rn(dy, k.reso1);
-        qz = __fdiv_rn(dz, k.zreso);
-    }
+// quotients -> integer keys (shared tail of the fast and the IEEE-division paths)
+__device__ __forceinline__ bool keys_from_quotients(float qx, float qy, float qz, float inten, const KParams &k,
+                                                    int &lrow, int &lcol, uint32_t &iq, uint32_t &zq) {
     const float rf = floorf(qx), cf = floorf(qy);
     const bool valid = (rf >= k.row_lo) && (rf < k.row_hi) && (cf >= k.col_lo) && (cf < k.col_hi);  // NaN -> false
     lrow = (int)rf - k.row0;
@@ -150,10 +138,42 @@ __device__ __forceinline__ bool quantise(const float4 p, const KParams &k, int &
     const float zf = fminf(fmaxf(rintf(qz), 0.0f), 255.0f);
     zq = (uint32_t)(int)zf;
     // clip of reference baseline/datasets/laserlane_proposals.py:626-628, then u8 mapping
-    const float ic = fminf(fmaxf(p.w, k.imin_f), k.imax_f);
+    const float ic = fminf(fmaxf(inten, k.imin_f), k.imax_f);
     const uint32_t n = (uint32_t)((int)ic - k.imin) * 65280u;     // ((I-imin)*255) << 8, < 2^32
     iq = __umulhi(n, k.imagic) >> k.ishift;                        // == (I-imin)*255 / (imax-imin)
     return valid;
+}
+
+// the spec, literally: IEEE division (inverse of reference baseline/utils/coor_img2pc.py:136-139,150)
+__device__ __forceinline__ bool quantise_ieee(const float4 p, const KParams &k, int &lrow, int &lcol,
+                                              uint32_t &iq, uint32_t &zq) {
+    return keys_from_quotients(__fdiv_rn(__fsub_rn(p.x, k.off0), k.reso0), __fdiv_rn(__fsub_rn(p.y, k.off1), k.reso1),
+                               __fdiv_rn(__fsub_rn(p.z, k.zmin), k.zreso), p.w, k, lrow, lcol, iq, zq);
+}
+
+// same result through div_const; the caller must check that lo/hi (running min/max of the
+// dividends' magnitudes) stay inside [2^-40, 2^64) and redo the point with quantise_ieee otherwise
+__device__ __forceinline__ bool quantise_fast(const float4 p, const KParams &k, int &lrow, int &lcol,
+                                              uint32_t &iq, uint32_t &zq, float &lo, float &hi) {
+    const float dx = __fsub_rn(p.x, k.off0), dy = __fsub_rn(p.y, k.off1), dz = __fsub_rn(p.z, k.zmin);
+    lo = fminf(lo, fminf(fabsf(dx), fminf(fabsf(dy), fabsf(dz))));
+    hi = fmaxf(hi, fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz))));
+    return keys_from_quotients(div_const(dx, k.reso0, k.rreso0), div_const(dy, k.reso1, k.rreso1),
+                               div_const(dz, k.zreso, k.rzreso), p.w, k, lrow, lcol, iq, zq);
+}
+// NaN dividends propagate identically through both paths (fminf/fmaxf skip them), so only the
+// magnitudes of the finite ones have to be in range; an all-NaN thread fails the test and takes
+// the IEEE path.
+__device__ __forceinline__ bool fast_range_ok(float lo, float hi) { return lo >= 0x1p-40f && hi < 0x1p64f; }
+
+__device__ __forceinline__ bool quantise(const float4 p, const KParams &k, int &lrow, int &lcol,
+                                         uint32_t &iq, uint32_t &zq) {
+    if (k.fast_div) {
+        float lo = 0x1p100f, hi = 0.0f;
+        const bool v = quantise_fast(p, k, lrow, lcol, iq, zq, lo, hi);
+        if (fast_range_ok(lo, hi)) return v;
+    }
+    return quantise_ieee(p, k, lrow, lcol, iq, zq);
 }
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
@@ -165,10 +185,10 @@ __device__ __forceinline__ uint32_t channel_value(int ch, uint32_t cnt, uint32_t
                                                   uint32_t max_i, uint32_t min_z, uint32_t max_z) {
     switch (ch) {
         case LM_CH_MAX_I: return max_i;
-        case LM_CH_MEAN_I: return cnt ? (uint32_t)(((unsigned long long)sum_i + (cnt >> 1)) / cnt) : 0u;
+        case LM_CH_MEAN_I: return cnt ? (sum_i + (cnt >> 1)) / cnt : 0u;     // < 2^32 while cnt < 2^24
         case LM_CH_MIN_Z: return cnt ? min_z : 0u;
         case LM_CH_MAX_Z: return max_z;
-        case LM_CH_MEAN_Z: return cnt ? (uint32_t)(((unsigned long long)sum_z + (cnt >> 1)) / cnt) : 0u;
+        case LM_CH_MEAN_Z: return cnt ? (sum_z + (cnt >> 1)) / cnt : 0u;
         case LM_CH_DENSITY: return cnt < 255u ? cnt : 255u;
     }
     return 0u;
@@ -251,6 +271,31 @@ __global__ void crop_tiles_kernel(const uint8_t *__restrict__ img, int H, int W,
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy (global -> shared) completing on an mbarrier: one thread moves a whole batch
+// of packed point records; no per-thread address math, no registers held while in flight
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "LM_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra LM_DONE;\n"
+                 "bra LM_WAIT;\n"
+                 "LM_DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // LM_ALGO_BINNED stage 1: bin_points
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_t count, uint32_t tile) {
@@ -258,60 +303,116 @@ __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_
     atomicAdd(&ws.tile_nchunks[tile], 1u);
 }
 
-__global__ void __launch_bounds__(BIN_THREADS, 4) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
+// Open-chunk state of one CTA: {cur chunk id (0 = none), fill}.  Kept in shared memory when the tile
+// count allows (SMEM_STATE), so that the per-batch reservation step touches no global memory; the
+// chunk ids themselves come from a per-CTA stash refilled with ONE global atomic per STASH chunks,
+// issued at the top of a batch so that its latency hides behind the batch's loads and key math.
+constexpr int STASH = 256;            // chunk ids fetched per refill
+constexpr int STASH_LOW = 32;         // refill when fewer than this remain (the remainder is abandoned)
+constexpr int SMEM_STATE_MAX_T = 4096;
+
+template <bool SMEM_STATE, bool WARP_AGG>
+__global__ void __launch_bounds__(BIN_THREADS, 3) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
                                                                  long long n, Ws ws) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = kp.T;
     const int D = T < BIN_BATCH ? T : BIN_BATCH;              // max tiles one batch can touch
-    uint4 *desc = reinterpret_cast<uint4 *>(smem_raw);                       // [D] {start, dst0, room, dst1}
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                    // [BIN_BATCH] next batch, filled by TMA
+    uint4 *desc = reinterpret_cast<uint4 *>(stage + BIN_BATCH);              // [D] {start, dst0, room, dst1}
     uint2 *sorted = reinterpret_cast<uint2 *>(desc + D);                     // [BIN_BATCH] {rec, desc idx}
     uint32_t *hist = reinterpret_cast<uint32_t *>(sorted + BIN_BATCH);       // [T]
     uint32_t *touched = hist + T;                                            // [D]
+    uint2 *s_state = reinterpret_cast<uint2 *>(touched + D);                 // [T] if SMEM_STATE
     __shared__ uint32_t s_cnt[2][2];                                         // [parity]{n_touched, cursor}
+    __shared__ uint32_t s_stash[2];                                          // {next id, end id}
+    __shared__ __align__(8) uint64_t s_bar;                                  // TMA completion barrier
 
-    const int tid = threadIdx.x;
-    for (int t = tid; t < T; t += BIN_THREADS) hist[t] = 0;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    for (int t = tid; t < T; t += BIN_THREADS) {
+        hist[t] = 0;
+        if (SMEM_STATE) s_state[t] = make_uint2(0u, 0u);
+    }
     if (tid < 4) (&s_cnt[0][0])[tid] = 0;
+    if (tid < 2) s_stash[tid] = 0;
     __syncthreads();
 
     const long long nb = (n + BIN_BATCH - 1) / BIN_BATCH;
     const long long b0 = nb * blockIdx.x / gridDim.x, b1 = nb * (blockIdx.x + 1) / gridDim.x;
-    uint2 *my_state = ws.state + (size_t)blockIdx.x * T;
+    uint2 *g_state = ws.state + (size_t)blockIdx.x * T;
     unsigned long long my_valid = 0;   // thread 0 only
+    auto batch_points = [&](long long b) -> uint32_t {
+        const long long left = n - b * BIN_BATCH;
+        return (uint32_t)(left < BIN_BATCH ? left : BIN_BATCH);
+    };
+    if (tid == 0 && b0 < b1) bulk_load(stage, pts + b0 * BIN_BATCH, batch_points(b0) * 16u, &s_bar);
 
     for (long long b = b0; b < b1; ++b) {
         const int par = (int)((b - b0) & 1);
-        const long long base = b * BIN_BATCH;
+        const uint32_t npts = batch_points(b);
+        mbar_wait(&s_bar, (uint32_t)par);            // this batch's records have landed in `stage`
         float4 p[BIN_PPT];
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
-            const long long idx = base + j * BIN_THREADS + tid;
-            p[j] = idx < n ? ld_stream(pts + idx) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+            const uint32_t i = j * BIN_THREADS + tid;
+            p[j] = i < npts ? stage[i] : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
         }
+        // stash refill (thread 0): the atomic is in flight while everybody computes keys
+        uint32_t refill = 0;
+        const bool do_refill = tid == 0 && (int)(s_stash[1] - s_stash[0]) < STASH_LOW;
+        if (do_refill) refill = atomicAdd(&ws.ctl->pool_cursor, (uint32_t)STASH) + 1u;
+
         uint32_t rec[BIN_PPT], tl[BIN_PPT], rk[BIN_PPT];
+        {
+            int r[BIN_PPT], c[BIN_PPT];
+            uint32_t iq[BIN_PPT], zq[BIN_PPT];
+            bool ok[BIN_PPT];
+            float lo = 0x1p100f, hi = 0.0f;
 #pragma unroll
-        for (int j = 0; j < BIN_PPT; ++j) {
-            int r, c;
-            uint32_t iq, zq;
-            if (quantise(p[j], kp, r, c, iq, zq)) {
-                const uint32_t t = (uint32_t)((r >> kp.tile_h_log2) * kp.tiles_x + (c >> TILE_W_LOG2));
-                const uint32_t cell = (uint32_t)(((r & ((1 << kp.tile_h_log2) - 1)) << TILE_W_LOG2) | (c & (TILE_W - 1)));
-                rec[j] = (cell << 16) | (iq << 8) | zq;
-                tl[j] = t;
-                rk[j] = atomicAdd(&hist[t], 1u);
-                if (rk[j] == 0) touched[atomicAdd(&s_cnt[par][0], 1u)] = t;
-            } else {
-                tl[j] = INVALID_U32;
+            for (int j = 0; j < BIN_PPT; ++j) ok[j] = quantise_fast(p[j], kp, r[j], c[j], iq[j], zq[j], lo, hi);
+            if (!(kp.fast_div && fast_range_ok(lo, hi))) {      // rare: 0, denormal-scale, huge, inf or all-NaN dividends
+#pragma unroll
+                for (int j = 0; j < BIN_PPT; ++j) ok[j] = quantise_ieee(p[j], kp, r[j], c[j], iq[j], zq[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < BIN_PPT; ++j) {
+                const uint32_t t = (uint32_t)((r[j] >> kp.tile_h_log2) * kp.tiles_x + (c[j] >> TILE_W_LOG2));
+                const uint32_t cell = (uint32_t)(((r[j] & ((1 << kp.tile_h_log2) - 1)) << TILE_W_LOG2) | (c[j] & (TILE_W - 1)));
+                rec[j] = (cell << 16) | (iq[j] << 8) | zq[j];
+                tl[j] = ok[j] ? t : INVALID_U32;
             }
         }
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            if (WARP_AGG) {      // one shared-memory atomic per distinct tile in the warp
+                const uint32_t peers = __match_any_sync(0xffffffffu, tl[j]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t first = 0;
+                if (lane == leader && tl[j] != INVALID_U32) {
+                    first = atomicAdd(&hist[tl[j]], (uint32_t)__popc(peers));
+                    if (first == 0) touched[atomicAdd(&s_cnt[par][0], 1u)] = tl[j];
+                }
+                rk[j] = __shfl_sync(0xffffffffu, first, leader) + __popc(peers & ((1u << lane) - 1u));
+            } else if (tl[j] != INVALID_U32) {
+                rk[j] = atomicAdd(&hist[tl[j]], 1u);
+                if (rk[j] == 0) touched[atomicAdd(&s_cnt[par][0], 1u)] = tl[j];
+            }
+        }
+        if (do_refill) {
+            if (refill + STASH <= ws.pool_chunks) { s_stash[0] = refill; s_stash[1] = refill + STASH; }
+            else atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
+        }
         __syncthreads();
+        // everybody holds its records in registers: refill `stage` with the next batch while this
+        // one is sorted and written out
+        if (tid == 0 && b + 1 < b1) bulk_load(stage, pts + (b + 1) * BIN_BATCH, batch_points(b + 1) * 16u, &s_bar);
         // ---- one thread per touched tile: reserve a run in the sort buffer and in the tile's chunks
         const int nt = (int)s_cnt[par][0];
         for (int k = tid; k < nt; k += BIN_THREADS) {
             const uint32_t t = touched[k];
             const uint32_t c = hist[t];
             const uint32_t start = atomicAdd(&s_cnt[par][1], c);
-            uint2 st = __ldcg(&my_state[t]);
+            const uint2 st = SMEM_STATE ? s_state[t] : __ldcg(&g_state[t]);
             uint32_t cur = st.x, fill = st.y;
             const uint32_t room = cur ? (uint32_t)CHUNK_RECS - fill : 0u;
             const uint32_t dst0 = cur * (uint32_t)CHUNK_RECS + fill;
@@ -319,7 +420,9 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) bin_points_kernel(KParams kp, 
             if (c > room) {
                 const uint32_t rest = c - room;
                 const uint32_t n_new = (rest + CHUNK_RECS - 1) / CHUNK_RECS;
-                const uint32_t first = atomicAdd(&ws.ctl->pool_cursor, n_new) + 1u;   // ids start at 1
+                uint32_t first = atomicAdd(&s_stash[0], n_new);            // shared-memory stash first
+                if (first + n_new > s_stash[1])                            // stash ran dry in this batch: go global
+                    first = atomicAdd(&ws.ctl->pool_cursor, n_new) + 1u;
                 if (first + n_new > ws.pool_chunks) {
                     atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
                     fill = cur ? (uint32_t)CHUNK_RECS : 0u;     // records beyond `room` are dropped
@@ -333,7 +436,8 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) bin_points_kernel(KParams kp, 
             } else {
                 fill += c;
             }
-            __stcg(&my_state[t], make_uint2(cur, fill));
+            if (SMEM_STATE) s_state[t] = make_uint2(cur, fill);
+            else __stcg(&g_state[t], make_uint2(cur, fill));
             desc[k] = make_uint4(start, dst0, room, dst1);
             hist[t] = ((uint32_t)k << 16) | start;   // tile -> {descriptor index, run start} for the scatter
         }
@@ -363,7 +467,7 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) bin_points_kernel(KParams kp, 
     }
     // ---- retire this CTA's open chunks
     for (int t = tid; t < T; t += BIN_THREADS) {
-        const uint2 st = __ldcg(&my_state[t]);
+        const uint2 st = SMEM_STATE ? s_state[t] : __ldcg(&g_state[t]);
         if (st.x) publish_chunk(ws, st.x, st.y, (uint32_t)t);
     }
     if (tid == 0 && my_valid) atomicAdd((unsigned long long *)&ws.stats->n_valid, my_valid);
@@ -423,8 +527,10 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, int T) {
 __global__ void index_chunks_kernel(Ws ws) {
     if (ws.stats->error & LM_DEV_ERR_POOL) return;
     const uint32_t used = ws.ctl->pool_cursor;    // ids 1..used
-    for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= used; id += gridDim.x * blockDim.x) {
+    const uint32_t last = used < ws.pool_chunks - 1u ? used : ws.pool_chunks - 1u;
+    for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= last; id += gridDim.x * blockDim.x) {
         const uint2 m = ws.chunk_meta[id];
+        if (m.y == 0) continue;                      // abandoned stash id
         const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], 1u);
         ws.chunk_index[slot] = id | ((m.y - 1u) << 23);
     }
@@ -574,6 +680,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
 
         // ---- finish: raw planes out (halo tiles), then channels packed in place
         const size_t gcells = (size_t)kp.H * kp.W;
+        const int nch = kp.nch, ch0 = kp.ch[0], ch1 = kp.ch[1], ch2 = kp.ch[2], ch3 = kp.ch[3];
         bool overflow = false;
         for (int cell = tid; cell < cells; cell += RED_THREADS) {
             const int lr = cell >> TILE_W_LOG2, lc = cell & (TILE_W - 1);
@@ -583,7 +690,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             const uint32_t mi = (MASK & M_MAXI) ? a_maxi[cell] : 0u;
             const uint32_t nzr = (MASK & M_MINZ) ? a_minz[cell] : 0u;
             const uint32_t xz = (MASK & M_MAXZ) ? a_maxz[cell] : 0u;
-            const uint32_t nz = nzr ? 256u - nzr : 0u;
+            const uint32_t nz = nzr ? 256u - nzr : 0u;          // 0 for an empty cell, with or without a count plane
             overflow |= cnt >= (1u << 24);
             const bool inside = lr < nrows && lc < ncols;
             if (want_raw && inside) {
@@ -595,13 +702,21 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
                 out.acc[LM_ACC_MIN_Z * gcells + g] = nzr ? nz : INVALID_U32;
                 out.acc[LM_ACC_MAX_Z * gcells + g] = xz;
             }
-            uint32_t pk = 0;
-            for (int c = 0; c < kp.nch; ++c) {
-                // nz is already 0 for an empty cell, with or without a count plane
-                pk |= channel_value(kp.ch[c], kp.ch[c] == LM_CH_MIN_Z ? 1u : cnt, si, sz, mi, nz, xz) << (8 * c);
-            }
+            // every candidate channel once (sums stay < 2^32 while cnt < 2^24), then a select per output byte
+            const uint32_t half = cnt >> 1, div = cnt ? cnt : 1u;
+            const uint32_t mean_i = (MASK & M_SUMI) ? (si + half) / div : 0u;
+            const uint32_t mean_z = (MASK & M_SUMZ) ? (sz + half) / div : 0u;
+            const uint32_t dens = cnt < 255u ? cnt : 255u;
+            auto pick = [&](int ch) -> uint32_t {
+                return ch == LM_CH_MAX_I ? mi : ch == LM_CH_MEAN_I ? mean_i : ch == LM_CH_MIN_Z ? nz
+                     : ch == LM_CH_MAX_Z ? xz : ch == LM_CH_MEAN_Z ? mean_z : dens;
+            };
+            uint32_t pk = pick(ch0);
+            if (nch > 1) pk |= pick(ch1) << 8;
+            if (nch > 2) pk |= pick(ch2) << 16;
+            if (nch > 3) pk |= pick(ch3) << 24;
             if (out.proj && inside) {
-                for (int c = 0; c < kp.nch; ++c)
+                for (int c = 0; c < nch; ++c)
                     out.proj[((size_t)c * kp.H + grow0 + lr) * kp.W + gcol0 + lc] =
                         __fdiv_rn((float)((pk >> (8 * c)) & 0xFFu), 255.0f);
             }
@@ -684,7 +799,14 @@ int pick_mask(int need, bool count16) {
 }
 // tile height so that NW planes of 128 x TH u32 stay <= 96 KB: two reduce CTAs per SM overlap
 // one tile's zero/finish/write phases with the other's streaming phase
-int tile_h_log2_for(int mask) { const int nw = popc6(mask); return nw <= 1 ? 7 : (nw <= 3 ? 6 : 5); }
+int tile_h_log2_for(int mask) {
+    const int nw = popc6(mask);
+    if (const char *e = getenv("LM_BEV_TILE_H_LOG2")) {      // tuning knob (5..7); must keep NW planes <= 227 KB
+        const int v = atoi(e);
+        if (v >= 5 && v <= 7 && nw * (128 << v) * 4 <= 220 * 1024) return v;
+    }
+    return nw <= 1 ? 7 : (nw <= 3 ? 6 : 5);
+}
 
 int validate(const lm_bev_params *p) {
     if (!p) return fail(LM_ERR_INVALID, "params is NULL");
@@ -762,14 +884,17 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
     L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
-    L->off_state = o;   o = align_up(o + (size_t)L->bin_ctas * T * sizeof(uint2), 256);
-    L->zero_bytes = o;
-    const unsigned long long chunks = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS) +
-                                      (unsigned long long)L->bin_ctas * T + 2ull;
+    L->off_state = o;   o = align_up(o + (T > SMEM_STATE_MAX_T ? (size_t)L->bin_ctas * T * sizeof(uint2) : 0), 256);
+    // full chunks + one open chunk per (CTA, tile) + chunk ids a CTA may abandon in its stash
+    const unsigned long long full = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS);
+    const unsigned long long chunks = full + full / (STASH / STASH_LOW) +
+                                      (unsigned long long)L->bin_ctas * ((unsigned long long)T + 2 * STASH) + 2ull;
     if (chunks >= (1ull << 23))     // chunk ids are 23-bit (index entries), record indices 32-bit
         return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^23 chunks: shard the call (fewer points or a smaller row window)");
     L->pool_chunks = (uint32_t)chunks;
+    // the side table is zeroed too: count == 0 marks chunk ids that were handed out but never used
     L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
+    L->zero_bytes = o;
     L->off_index = o; o = align_up(o + (size_t)chunks * 4, 256);
     L->off_pool = o;  o = align_up(o + (size_t)chunks * CHUNK_RECS * 4, 256);
     L->total = o;
@@ -778,7 +903,8 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
 
 size_t bin_smem_bytes(int T) {
     const int D = T < BIN_BATCH ? T : BIN_BATCH;
-    return (size_t)D * sizeof(uint4) + (size_t)BIN_BATCH * sizeof(uint2) + (size_t)T * 4 + (size_t)D * 4;
+    return (size_t)BIN_BATCH * sizeof(float4) + (size_t)D * sizeof(uint4) + (size_t)BIN_BATCH * sizeof(uint2) +
+           (size_t)T * 4 + (size_t)D * 4 + (T <= SMEM_STATE_MAX_T ? (size_t)T * sizeof(uint2) : 0);
 }
 
 template <int MASK>
@@ -914,9 +1040,13 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
         if (e != cudaSuccess) return cuda_fail(e, "memset");
         if (n_points > 0) {
             const size_t smem = bin_smem_bytes(kp.T);
-            e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const char *agg_env = getenv("LM_BEV_WARP_AGG");      // tuning knob, default off: MATCH.ANY costs more than the conflicts it saves
+            const bool agg = agg_env && atoi(agg_env) != 0;
+            auto kern = kp.T <= SMEM_STATE_MAX_T ? (agg ? bin_points_kernel<true, true> : bin_points_kernel<true, false>)
+                                                 : (agg ? bin_points_kernel<false, true> : bin_points_kernel<false, false>);
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-            bin_points_kernel<<<L.bin_ctas, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+            kern<<<L.bin_ctas, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
         }
     }
     if (stages & LM_STAGE_INDEX) {
