@@ -42,7 +42,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into csrc/liblm_bev.so; returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, *SOURCES]
+    extra = os.environ.get("LM_BEV_NVCC_EXTRA", "").split()      # tuning builds, e.g. -DLM_BIN_THREADS=256
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

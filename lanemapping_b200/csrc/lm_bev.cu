@@ -36,8 +36,17 @@ namespace {
 constexpr int TILE_W_LOG2 = 7;            // shared-memory tile: 128 cols x (128 | 64) rows
 constexpr int TILE_W = 1 << TILE_W_LOG2;
 constexpr int CHUNK_RECS = 512;           // records per pool chunk (2 KB)
-constexpr int BIN_THREADS = 256;
-constexpr int BIN_PPT = 8;                // points per thread per batch
+#ifndef LM_BIN_THREADS
+#define LM_BIN_THREADS 512
+#endif
+#ifndef LM_BIN_PPT
+#define LM_BIN_PPT 4
+#endif
+#ifndef LM_BIN_MIN_CTAS
+#define LM_BIN_MIN_CTAS 2
+#endif
+constexpr int BIN_THREADS = LM_BIN_THREADS;
+constexpr int BIN_PPT = LM_BIN_PPT;       // points per thread per batch
 constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
 constexpr int MAX_BIN_CTAS = 148 * 4;     // sizing constant of the workspace (B200: 148 SMs)
 constexpr int RED_THREADS = 512;
@@ -312,7 +321,7 @@ constexpr int STASH_LOW = 32;         // refill when fewer than this remain (the
 constexpr int SMEM_STATE_MAX_T = 4096;
 
 template <bool SMEM_STATE, bool WARP_AGG>
-__global__ void __launch_bounds__(BIN_THREADS, 3) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
+__global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
                                                                  long long n, Ws ws) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = kp.T;
@@ -454,12 +463,16 @@ __global__ void __launch_bounds__(BIN_THREADS, 3) bin_points_kernel(KParams kp, 
         __syncthreads();
         // ---- coalesced write-out: consecutive threads -> consecutive records of a run
         const int nv = (int)s_cnt[par][1];
-        for (int i = tid; i < nv; i += BIN_THREADS) {
-            const uint2 e = sorted[i];
-            const uint4 d = desc[e.y];
-            const uint32_t off = (uint32_t)i - d.x;
-            if (off < d.z) ws.pool[d.y + off] = e.x;
-            else if (d.w != INVALID_U32) ws.pool[d.w + (off - d.z)] = e.x;
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {          // independent iterations: the loads of all of them overlap
+            const int i = j * BIN_THREADS + tid;
+            if (i < nv) {
+                const uint2 e = sorted[i];
+                const uint4 d = desc[e.y];
+                const uint32_t off = (uint32_t)i - d.x;
+                if (off < d.z) ws.pool[d.y + off] = e.x;
+                else if (d.w != INVALID_U32) ws.pool[d.w + (off - d.z)] = e.x;
+            }
         }
         for (int k = tid; k < nt; k += BIN_THREADS) hist[touched[k]] = 0;
         if (tid == 0) my_valid += (unsigned long long)nv;
