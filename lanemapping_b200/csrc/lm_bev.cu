@@ -37,21 +37,21 @@ constexpr int TILE_W_LOG2 = 7;            // shared-memory tile: 128 cols x (128
 constexpr int TILE_W = 1 << TILE_W_LOG2;
 constexpr int CHUNK_RECS = 512;           // records per pool chunk (2 KB)
 #ifndef LM_BIN_THREADS
-#define LM_BIN_THREADS 512
+#define LM_BIN_THREADS 256
 #endif
 #ifndef LM_BIN_PPT
 #define LM_BIN_PPT 4
 #endif
 #ifndef LM_BIN_MIN_CTAS
-#define LM_BIN_MIN_CTAS 2
+#define LM_BIN_MIN_CTAS 4
 #endif
 constexpr int BIN_THREADS = LM_BIN_THREADS;
 constexpr int BIN_PPT = LM_BIN_PPT;       // points per thread per batch
 constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
-constexpr int MAX_BIN_CTAS = 148 * 4;     // sizing constant of the workspace (B200: 148 SMs)
+constexpr int MAX_BIN_CTAS = 148 * LM_BIN_MIN_CTAS;   // sizing constant of the workspace (B200: 148 SMs)
 constexpr int RED_THREADS = 512;
 constexpr int RED_MIN_CTAS = 2;          // shared-memory tiles are sized so that two CTAs fit per SM
-constexpr int MAX_TILES = 40000;          // limit of bin_points' shared-memory histogram
+constexpr int MAX_TILES = 9000;           // bin_points keeps 20 B of append state per tile in shared memory
 constexpr uint32_t INVALID_U32 = 0xFFFFFFFFu;
 
 // accumulator planes held in shared memory by reduce_tiles (bit mask)
@@ -69,8 +69,7 @@ struct KParams {
     float row_lo, row_hi, col_lo, col_hi;
     float rreso0, rreso1, rzreso;   // RN(1/reso): operands of the exact 3-op division
     int fast_div;                   // all three divisors in the range div_const is proven for
-    float imin_f, imax_f;
-    int imin;
+    int imin, imax;
     uint32_t imagic, ishift;        // n/d == umulhi(n << 8, imagic) >> ishift for n < 2^24
     int nch;
     int ch[4];
@@ -90,7 +89,6 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t *tile_first;    // [T]
     uint32_t *tile_cursor;   // [T]
     uint32_t *tile_order;    // [T] tiles sorted heaviest first (reduce_tiles schedule)
-    uint2 *state;            // [MAX_BIN_CTAS][T] {cur chunk id, fill}
     uint2 *chunk_meta;       // [P] {tile, count}
     uint32_t *chunk_index;   // [P] per-tile chunk lists: id | (count-1) << 23
     uint32_t *pool;          // [P][CHUNK_RECS]
@@ -136,19 +134,24 @@ __device__ __forceinline__ float div_const(float a, float c, float rc) {
 // the dividends the fast path accepts: finite magnitudes in [2^-40, 2^64)
 __device__ __forceinline__ bool div_fast_ok(float a) { return fabsf(a) >= 0x1p-40f && fabsf(a) < 0x1p64f; }
 
-// quotients -> integer keys (shared tail of the fast and the IEEE-division paths)
+// quotients -> integer keys (shared tail of the fast and the IEEE-division paths).
+// The conversions use the saturating F2I modes, which give the same integers as the spec's
+// floorf / rintf / clamp-then-truncate on every input (huge values saturate and fall outside the
+// window or into the clamp; NaN converts to 0 and is rejected / clamped exactly as fmaxf would).
 __device__ __forceinline__ bool keys_from_quotients(float qx, float qy, float qz, float inten, const KParams &k,
                                                     int &lrow, int &lcol, uint32_t &iq, uint32_t &zq) {
-    const float rf = floorf(qx), cf = floorf(qy);
-    const bool valid = (rf >= k.row_lo) && (rf < k.row_hi) && (cf >= k.col_lo) && (cf < k.col_hi);  // NaN -> false
-    lrow = (int)rf - k.row0;
-    lcol = (int)cf - k.col0;
-    // inverse of coor_img2pc.py:150, round-half-even; NaN -> 0 through fmaxf
-    const float zf = fminf(fmaxf(rintf(qz), 0.0f), 255.0f);
-    zq = (uint32_t)(int)zf;
-    // clip of reference baseline/datasets/laserlane_proposals.py:626-628, then u8 mapping
-    const float ic = fminf(fmaxf(inten, k.imin_f), k.imax_f);
-    const uint32_t n = (uint32_t)((int)ic - k.imin) * 65280u;     // ((I-imin)*255) << 8, < 2^32
+    const uint32_t ur = (uint32_t)__float2int_rd(qx) - (uint32_t)k.row0;      // floor, then window shift
+    const uint32_t uc = (uint32_t)__float2int_rd(qy) - (uint32_t)k.col0;
+    const float s = __fadd_rn(qx, qy);                                        // NaN iff a quotient is NaN
+    const bool valid = ur < (uint32_t)k.H && uc < (uint32_t)k.W && s == s;    // never clamped, NaN dropped
+    lrow = (int)ur;
+    lcol = (int)uc;
+    // inverse of coor_img2pc.py:150: round-half-even, clamp to the u8 range, NaN -> 0
+    zq = (uint32_t)min(max(__float2int_rn(qz), 0), 255);
+    // clip of reference baseline/datasets/laserlane_proposals.py:626-628 (bounds are integers, so
+    // clamping after the truncation is the same), then the u8 mapping
+    const int iv = min(max(__float2int_rz(inten), k.imin), k.imax);
+    const uint32_t n = (uint32_t)(iv - k.imin) * 65280u;          // ((I-imin)*255) << 8, < 2^32
     iq = __umulhi(n, k.imagic) >> k.ishift;                        // == (I-imin)*255 / (imax-imin)
     return valid;
 }
@@ -286,11 +289,11 @@ __global__ void crop_tiles_kernel(const uint8_t *__restrict__ img, int H, int W,
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -304,6 +307,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                  "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Shared-memory accesses of the hot loop go through explicit 32-bit shared addresses: the base is
+// computed once and stays in a register (the generic form re-derives the shared window per access).
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+
 // ------------------------------------------------------------------------------------------
 // LM_ALGO_BINNED stage 1: bin_points
 // ------------------------------------------------------------------------------------------
@@ -312,66 +336,71 @@ __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_
     atomicAdd(&ws.tile_nchunks[tile], 1u);
 }
 
-// Open-chunk state of one CTA: {cur chunk id (0 = none), fill}.  Kept in shared memory when the tile
-// count allows (SMEM_STATE), so that the per-batch reservation step touches no global memory; the
-// chunk ids themselves come from a per-CTA stash refilled with ONE global atomic per STASH chunks,
-// issued at the top of a batch so that its latency hides behind the batch's loads and key math.
-constexpr int STASH = 256;            // chunk ids fetched per refill
+// Per-CTA append state, all in shared memory:
+//   pos[t]      how many records this CTA has appended to tile t so far (monotonic over the kernel)
+//   slot[t][4]  ring of chunk ids: record number q of tile t lives in chunk slot[t][(q / CHUNK) & 3]
+// A point's atomicAdd on pos[t] IS its reservation: it yields the chunk-block and the offset inside
+// it.  The thread that draws the first record of a block allocates that block's chunk (from a
+// per-CTA stash of ids refilled with one global atomic per STASH chunks).  Nothing in a batch is
+// serial: two balanced phases (reserve / store) separated by one barrier each.
+// A batch appends at most BIN_BATCH <= 2 * CHUNK records to a tile, i.e. it starts at most two new
+// blocks, so four ring slots can never wrap inside the window that is still being read.
+constexpr int CHUNK_LOG2 = 9;
+static_assert((1 << CHUNK_LOG2) == CHUNK_RECS, "CHUNK_LOG2");
+static_assert(BIN_BATCH <= 2 * CHUNK_RECS, "a batch may start at most two chunk blocks per tile");
+constexpr int NSLOT = 4;
+constexpr int STASH = 128;            // chunk ids fetched per refill
 constexpr int STASH_LOW = 32;         // refill when fewer than this remain (the remainder is abandoned)
-constexpr int SMEM_STATE_MAX_T = 4096;
 
-template <bool SMEM_STATE, bool WARP_AGG>
 __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
-                                                                 long long n, Ws ws) {
+                                                                               long long n, Ws ws) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = kp.T;
-    const int D = T < BIN_BATCH ? T : BIN_BATCH;              // max tiles one batch can touch
-    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                    // [BIN_BATCH] next batch, filled by TMA
-    uint4 *desc = reinterpret_cast<uint4 *>(stage + BIN_BATCH);              // [D] {start, dst0, room, dst1}
-    uint2 *sorted = reinterpret_cast<uint2 *>(desc + D);                     // [BIN_BATCH] {rec, desc idx}
-    uint32_t *hist = reinterpret_cast<uint32_t *>(sorted + BIN_BATCH);       // [T]
-    uint32_t *touched = hist + T;                                            // [D]
-    uint2 *s_state = reinterpret_cast<uint2 *>(touched + D);                 // [T] if SMEM_STATE
-    __shared__ uint32_t s_cnt[2][2];                                         // [parity]{n_touched, cursor}
-    __shared__ uint32_t s_stash[2];                                          // {next id, end id}
-    __shared__ __align__(8) uint64_t s_bar;                                  // TMA completion barrier
+    // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u32
+    const uint32_t sm_stage = smem_u32(smem_raw);
+    const uint32_t sm_pos = sm_stage + 2u * BIN_BATCH * 16u;
+    const uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
+    __shared__ uint32_t s_stash[2][2];                                       // [which]{next id, end id}
+    __shared__ uint32_t s_active;                                            // which stash phase 1 draws from
+    __shared__ __align__(8) uint64_t s_bar[2];                               // TMA completion barriers
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) mbar_init(&s_bar, 1);
-    for (int t = tid; t < T; t += BIN_THREADS) {
-        hist[t] = 0;
-        if (SMEM_STATE) s_state[t] = make_uint2(0u, 0u);
-    }
-    if (tid < 4) (&s_cnt[0][0])[tid] = 0;
-    if (tid < 2) s_stash[tid] = 0;
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_active = 0; }
+    if (tid < 4) (&s_stash[0][0])[tid] = 0;
+    for (int t = tid; t < T; t += BIN_THREADS) sts_u32(sm_pos + 4u * t, 0u);
     __syncthreads();
 
     const long long nb = (n + BIN_BATCH - 1) / BIN_BATCH;
     const long long b0 = nb * blockIdx.x / gridDim.x, b1 = nb * (blockIdx.x + 1) / gridDim.x;
-    uint2 *g_state = ws.state + (size_t)blockIdx.x * T;
-    unsigned long long my_valid = 0;   // thread 0 only
-    auto batch_points = [&](long long b) -> uint32_t {
-        const long long left = n - b * BIN_BATCH;
-        return (uint32_t)(left < BIN_BATCH ? left : BIN_BATCH);
-    };
-    if (tid == 0 && b0 < b1) bulk_load(stage, pts + b0 * BIN_BATCH, batch_points(b0) * 16u, &s_bar);
+    const int my_batches = (int)(b1 - b0);
+    const float4 *src = pts + b0 * BIN_BATCH;                                // this CTA's contiguous range
+    const uint32_t tail = (uint32_t)(n - (nb - 1) * BIN_BATCH);             // points in the very last batch
+    auto batch_points = [&](int k) -> uint32_t { return b0 + k == nb - 1 ? tail : (uint32_t)BIN_BATCH; };
+    if (tid == 0 && my_batches > 0) bulk_load(smem_raw, src, batch_points(0) * 16u, &s_bar[0]);
 
-    for (long long b = b0; b < b1; ++b) {
-        const int par = (int)((b - b0) & 1);
-        const uint32_t npts = batch_points(b);
-        mbar_wait(&s_bar, (uint32_t)par);            // this batch's records have landed in `stage`
-        float4 p[BIN_PPT];
-#pragma unroll
-        for (int j = 0; j < BIN_PPT; ++j) {
-            const uint32_t i = j * BIN_THREADS + tid;
-            p[j] = i < npts ? stage[i] : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
-        }
-        // stash refill (thread 0): the atomic is in flight while everybody computes keys
+    for (int k = 0; k < my_batches; ++k) {
+        const uint32_t buf = (uint32_t)k & 1u;
+        // the NEXT batch starts flying now, into the buffer that was consumed one batch ago
+        if (tid == 0 && k + 1 < my_batches)
+            bulk_load(smem_raw + (buf ^ 1u) * (BIN_BATCH * 16u), src + (size_t)(k + 1) * BIN_BATCH,
+                      batch_points(k + 1) * 16u, &s_bar[buf ^ 1u]);
+        // stash refill (thread 0): the global atomic is in flight while everybody computes keys
+        const uint32_t act = s_active;
         uint32_t refill = 0;
-        const bool do_refill = tid == 0 && (int)(s_stash[1] - s_stash[0]) < STASH_LOW;
+        const bool do_refill = tid == 0 && (int)(s_stash[act][1] - s_stash[act][0]) < STASH_LOW;
         if (do_refill) refill = atomicAdd(&ws.ctl->pool_cursor, (uint32_t)STASH) + 1u;
 
-        uint32_t rec[BIN_PPT], tl[BIN_PPT], rk[BIN_PPT];
+        const uint32_t npts = batch_points(k);
+        mbar_wait(&s_bar[buf], ((uint32_t)k >> 1) & 1u);     // this batch's records have landed
+        float4 p[BIN_PPT];
+        const uint32_t my_stage = sm_stage + buf * (BIN_BATCH * 16u) + (uint32_t)tid * 16u;
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            p[j] = lds_f4(my_stage + (uint32_t)j * (BIN_THREADS * 16u));
+            if ((uint32_t)(j * BIN_THREADS + tid) >= npts) p[j].x = __int_as_float(0x7fc00000);   // NaN x: dropped
+        }
+
+        uint32_t rec[BIN_PPT], tl[BIN_PPT], ps[BIN_PPT];
         {
             int r[BIN_PPT], c[BIN_PPT];
             uint32_t iq[BIN_PPT], zq[BIN_PPT];
@@ -391,99 +420,65 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
                 tl[j] = ok[j] ? t : INVALID_U32;
             }
         }
-#pragma unroll
-        for (int j = 0; j < BIN_PPT; ++j) {
-            if (WARP_AGG) {      // one shared-memory atomic per distinct tile in the warp
-                const uint32_t peers = __match_any_sync(0xffffffffu, tl[j]);
-                const int leader = __ffs(peers) - 1;
-                uint32_t first = 0;
-                if (lane == leader && tl[j] != INVALID_U32) {
-                    first = atomicAdd(&hist[tl[j]], (uint32_t)__popc(peers));
-                    if (first == 0) touched[atomicAdd(&s_cnt[par][0], 1u)] = tl[j];
-                }
-                rk[j] = __shfl_sync(0xffffffffu, first, leader) + __popc(peers & ((1u << lane) - 1u));
-            } else if (tl[j] != INVALID_U32) {
-                rk[j] = atomicAdd(&hist[tl[j]], 1u);
-                if (rk[j] == 0) touched[atomicAdd(&s_cnt[par][0], 1u)] = tl[j];
-            }
-        }
-        if (do_refill) {
-            if (refill + STASH <= ws.pool_chunks) { s_stash[0] = refill; s_stash[1] = refill + STASH; }
-            else atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
-        }
-        __syncthreads();
-        // everybody holds its records in registers: refill `stage` with the next batch while this
-        // one is sorted and written out
-        if (tid == 0 && b + 1 < b1) bulk_load(stage, pts + (b + 1) * BIN_BATCH, batch_points(b + 1) * 16u, &s_bar);
-        // ---- one thread per touched tile: reserve a run in the sort buffer and in the tile's chunks
-        const int nt = (int)s_cnt[par][0];
-        for (int k = tid; k < nt; k += BIN_THREADS) {
-            const uint32_t t = touched[k];
-            const uint32_t c = hist[t];
-            const uint32_t start = atomicAdd(&s_cnt[par][1], c);
-            const uint2 st = SMEM_STATE ? s_state[t] : __ldcg(&g_state[t]);
-            uint32_t cur = st.x, fill = st.y;
-            const uint32_t room = cur ? (uint32_t)CHUNK_RECS - fill : 0u;
-            const uint32_t dst0 = cur * (uint32_t)CHUNK_RECS + fill;
-            uint32_t dst1 = INVALID_U32;
-            if (c > room) {
-                const uint32_t rest = c - room;
-                const uint32_t n_new = (rest + CHUNK_RECS - 1) / CHUNK_RECS;
-                uint32_t first = atomicAdd(&s_stash[0], n_new);            // shared-memory stash first
-                if (first + n_new > s_stash[1])                            // stash ran dry in this batch: go global
-                    first = atomicAdd(&ws.ctl->pool_cursor, n_new) + 1u;
-                if (first + n_new > ws.pool_chunks) {
-                    atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
-                    fill = cur ? (uint32_t)CHUNK_RECS : 0u;     // records beyond `room` are dropped
-                } else {
-                    if (cur) publish_chunk(ws, cur, CHUNK_RECS, t);
-                    for (uint32_t q = 0; q + 1 < n_new; ++q) publish_chunk(ws, first + q, CHUNK_RECS, t);
-                    cur = first + n_new - 1;
-                    fill = rest - (n_new - 1) * CHUNK_RECS;
-                    dst1 = first * (uint32_t)CHUNK_RECS;
-                }
-            } else {
-                fill += c;
-            }
-            if (SMEM_STATE) s_state[t] = make_uint2(cur, fill);
-            else __stcg(&g_state[t], make_uint2(cur, fill));
-            desc[k] = make_uint4(start, dst0, room, dst1);
-            hist[t] = ((uint32_t)k << 16) | start;   // tile -> {descriptor index, run start} for the scatter
-        }
-        if (tid == 0) { s_cnt[par ^ 1][0] = 0; s_cnt[par ^ 1][1] = 0; }
-        __syncthreads();
-        // ---- scatter records into tile-sorted order (shared memory)
+        // ---- phase 1: reserve.  The first record of a chunk block allocates the block's chunk.
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
-                const uint32_t h = hist[tl[j]];
-                sorted[(h & 0xFFFFu) + rk[j]] = make_uint2(rec[j], h >> 16);
+                ps[j] = atoms_add(sm_pos + 4u * tl[j], 1u);
+                if ((ps[j] & (CHUNK_RECS - 1)) == 0) {
+                    uint32_t id = atomicAdd(&s_stash[act][0], 1u);
+                    if (id >= s_stash[act][1]) id = atomicAdd(&ws.ctl->pool_cursor, 1u) + 1u;     // stash dry: go global
+                    if (id >= ws.pool_chunks) {                  // cannot happen with lm_bev_workspace_bytes' size
+                        atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
+                        id = 0;                                  // chunk 0 is a scratch chunk nobody reads
+                    }
+                    sts_u32(sm_slot + 4u * (tl[j] * NSLOT + ((ps[j] >> CHUNK_LOG2) & (NSLOT - 1))), id);
+                }
             }
         }
         __syncthreads();
-        // ---- coalesced write-out: consecutive threads -> consecutive records of a run
-        const int nv = (int)s_cnt[par][1];
+        // install the refilled stash for the next reserve phase (nobody allocates in phase 2)
+        if (do_refill) {
+            if (refill + STASH <= ws.pool_chunks) {
+                s_stash[act ^ 1][0] = refill;
+                s_stash[act ^ 1][1] = refill + STASH;
+                s_active = act ^ 1;
+            } else {
+                atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
+            }
+        }
+        // ---- phase 2: store.  Lanes that hit the same tile drew consecutive positions, so they write
+        //      neighbouring words; L2 merges partial sectors before they reach HBM.
+        uint32_t cid[BIN_PPT];
 #pragma unroll
-        for (int j = 0; j < BIN_PPT; ++j) {          // independent iterations: the loads of all of them overlap
-            const int i = j * BIN_THREADS + tid;
-            if (i < nv) {
-                const uint2 e = sorted[i];
-                const uint4 d = desc[e.y];
-                const uint32_t off = (uint32_t)i - d.x;
-                if (off < d.z) ws.pool[d.y + off] = e.x;
-                else if (d.w != INVALID_U32) ws.pool[d.w + (off - d.z)] = e.x;
+        for (int j = 0; j < BIN_PPT; ++j)
+            cid[j] = tl[j] != INVALID_U32 ? lds_u32(sm_slot + 4u * (tl[j] * NSLOT + ((ps[j] >> CHUNK_LOG2) & (NSLOT - 1)))) : 0u;
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            if (tl[j] != INVALID_U32) {
+                const uint32_t off = ps[j] & (CHUNK_RECS - 1);
+                ws.pool[cid[j] * (uint32_t)CHUNK_RECS + off] = rec[j];        // record index < 2^32 (checked on the host)
+                if (off == 0 && ps[j] != 0) {                    // the previous block of this tile is complete
+                    const uint32_t prev = lds_u32(sm_slot + 4u * (tl[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
+                    if (prev) publish_chunk(ws, prev, CHUNK_RECS, tl[j]);
+                }
             }
         }
-        for (int k = tid; k < nt; k += BIN_THREADS) hist[touched[k]] = 0;
-        if (tid == 0) my_valid += (unsigned long long)nv;
         __syncthreads();
     }
-    // ---- retire this CTA's open chunks
+    // ---- retire this CTA's open chunks; the final positions also give the number of points kept
+    uint32_t my_valid = 0;
     for (int t = tid; t < T; t += BIN_THREADS) {
-        const uint2 st = SMEM_STATE ? s_state[t] : __ldcg(&g_state[t]);
-        if (st.x) publish_chunk(ws, st.x, st.y, (uint32_t)t);
+        const uint32_t q = lds_u32(sm_pos + 4u * t);
+        if (q) {
+            my_valid += q;
+            const uint32_t last = q - 1;
+            const uint32_t id = lds_u32(sm_slot + 4u * (t * NSLOT + ((last >> CHUNK_LOG2) & (NSLOT - 1))));
+            if (id) publish_chunk(ws, id, (last & (CHUNK_RECS - 1)) + 1u, (uint32_t)t);
+        }
     }
-    if (tid == 0 && my_valid) atomicAdd((unsigned long long *)&ws.stats->n_valid, my_valid);
+    for (int o = 16; o; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
+    if ((tid & 31) == 0 && my_valid) atomicAdd((unsigned long long *)&ws.stats->n_valid, (unsigned long long)my_valid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -846,7 +841,7 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     k.zmin = p->local_min_ele; k.zreso = p->ele_reso;
     k.row_lo = (float)p->row0; k.row_hi = (float)(p->row0 + p->height);
     k.col_lo = (float)p->col0; k.col_hi = (float)(p->col0 + p->width);
-    k.imin_f = (float)p->inten_min; k.imax_f = (float)p->inten_max; k.imin = p->inten_min;
+    k.imin = p->inten_min; k.imax = p->inten_max;
     // exact n/d for n < 2^24 (Granlund-Montgomery): l = ceil(log2 d), m = ceil(2^(24+l)/d) < 2^25,
     // n/d = floor(n*m / 2^(24+l)) = umulhi(n << 8, m) >> l
     const unsigned long long d = (unsigned long long)(p->inten_max - p->inten_min);
@@ -867,7 +862,7 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
 }
 
 struct Layout {
-    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, off_state, zero_bytes;
+    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, zero_bytes;
     size_t off_meta, off_index, off_pool, off_acc, total;
     uint32_t pool_chunks;
     int bin_ctas;
@@ -897,12 +892,11 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
     L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
-    L->off_state = o;   o = align_up(o + (T > SMEM_STATE_MAX_T ? (size_t)L->bin_ctas * T * sizeof(uint2) : 0), 256);
     // full chunks + one open chunk per (CTA, tile) + chunk ids a CTA may abandon in its stash
     const unsigned long long full = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS);
     const unsigned long long chunks = full + full / (STASH / STASH_LOW) +
-                                      (unsigned long long)L->bin_ctas * ((unsigned long long)T + 2 * STASH) + 2ull;
-    if (chunks >= (1ull << 23))     // chunk ids are 23-bit (index entries), record indices 32-bit
+                                      (unsigned long long)MAX_BIN_CTAS * ((unsigned long long)T + 2 * STASH) + 2ull;
+    if (chunks >= (1ull << 23))     // chunk ids are 23-bit (index entries), record indices 32-bit (2^23 * 512 = 2^32)
         return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^23 chunks: shard the call (fewer points or a smaller row window)");
     L->pool_chunks = (uint32_t)chunks;
     // the side table is zeroed too: count == 0 marks chunk ids that were handed out but never used
@@ -914,11 +908,7 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     return LM_OK;
 }
 
-size_t bin_smem_bytes(int T) {
-    const int D = T < BIN_BATCH ? T : BIN_BATCH;
-    return (size_t)BIN_BATCH * sizeof(float4) + (size_t)D * sizeof(uint4) + (size_t)BIN_BATCH * sizeof(uint2) +
-           (size_t)T * 4 + (size_t)D * 4 + (T <= SMEM_STATE_MAX_T ? (size_t)T * sizeof(uint2) : 0);
-}
+size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * 4 * (1 + NSLOT); }
 
 template <int MASK>
 cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sms, cudaStream_t st) {
@@ -1040,7 +1030,6 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
     ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
     ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
     ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
-    ws.state = reinterpret_cast<uint2 *>(w + L.off_state);
     ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
     ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
     ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
@@ -1053,13 +1042,17 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
         if (e != cudaSuccess) return cuda_fail(e, "memset");
         if (n_points > 0) {
             const size_t smem = bin_smem_bytes(kp.T);
-            const char *agg_env = getenv("LM_BEV_WARP_AGG");      // tuning knob, default off: MATCH.ANY costs more than the conflicts it saves
-            const bool agg = agg_env && atoi(agg_env) != 0;
-            auto kern = kp.T <= SMEM_STATE_MAX_T ? (agg ? bin_points_kernel<true, true> : bin_points_kernel<true, false>)
-                                                 : (agg ? bin_points_kernel<false, true> : bin_points_kernel<false, false>);
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-            kern<<<L.bin_ctas, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+            // persistent: one wave of resident CTAs, each owning a contiguous range of batches
+            int occ = 1;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_kernel, BIN_THREADS, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
+            long long grid = (long long)sms * (occ < 1 ? 1 : occ);
+            if (grid > MAX_BIN_CTAS) grid = MAX_BIN_CTAS;
+            const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
+            if (grid > nb) grid = nb;
+            bin_points_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
         }
     }
     if (stages & LM_STAGE_INDEX) {
