@@ -43,7 +43,7 @@ constexpr int CHUNK_RECS = 512;           // records per pool chunk (2 KB)
 #define LM_BIN_PPT 4
 #endif
 #ifndef LM_BIN_MIN_CTAS
-#define LM_BIN_MIN_CTAS 4
+#define LM_BIN_MIN_CTAS 3
 #endif
 constexpr int BIN_THREADS = LM_BIN_THREADS;
 constexpr int BIN_PPT = LM_BIN_PPT;       // points per thread per batch
@@ -74,6 +74,8 @@ struct KParams {
     int nch;
     int ch[4];
     int tile_h_log2, tiles_x, tiles_y, T;
+    int oH, orow;   // height of the output buffers and this window's first row inside them
+                    // (a raster with more tiles than one launch handles is done as row windows)
 };
 
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
@@ -627,8 +629,9 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         const int nrows = min(TH, kp.H - grow0), ncols = min(TILE_W, kp.W - gcol0);
         const uint32_t nchunks = ws.tile_nchunks[t];
         const uint32_t *my_index = ws.chunk_index + ws.tile_first[t];
+        const int orow0 = kp.orow + grow0;                       // first row of this tile in the output buffers
         const bool want_raw = out.acc != nullptr &&
-                              (out.acc_band <= 0 || grow0 < out.acc_band || grow0 + nrows > kp.H - out.acc_band);
+                              (out.acc_band <= 0 || orow0 < out.acc_band || orow0 + nrows > kp.oH - out.acc_band);
 
         // first chunk of this warp: issue its loads before zeroing so the latency overlaps
         uint32_t c = warp;
@@ -687,7 +690,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         __syncthreads();
 
         // ---- finish: raw planes out (halo tiles), then channels packed in place
-        const size_t gcells = (size_t)kp.H * kp.W;
+        const size_t gcells = (size_t)kp.oH * kp.W;
         const int nch = kp.nch, ch0 = kp.ch[0], ch1 = kp.ch[1], ch2 = kp.ch[2], ch3 = kp.ch[3];
         bool overflow = false;
         for (int cell = tid; cell < cells; cell += RED_THREADS) {
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             overflow |= cnt >= (1u << 24);
             const bool inside = lr < nrows && lc < ncols;
             if (want_raw && inside) {
-                const size_t g = (size_t)(grow0 + lr) * kp.W + gcol0 + lc;
+                const size_t g = (size_t)(orow0 + lr) * kp.W + gcol0 + lc;
                 out.acc[LM_ACC_COUNT * gcells + g] = cnt;
                 out.acc[LM_ACC_SUM_I * gcells + g] = si;
                 out.acc[LM_ACC_SUM_Z * gcells + g] = sz;
@@ -725,7 +728,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             if (nch > 3) pk |= pick(ch3) << 24;
             if (out.proj && inside) {
                 for (int c = 0; c < nch; ++c)
-                    out.proj[((size_t)c * kp.H + grow0 + lr) * kp.W + gcol0 + lc] =
+                    out.proj[((size_t)c * kp.oH + orow0 + lr) * kp.W + gcol0 + lc] =
                         __fdiv_rn((float)((pk >> (8 * c)) & 0xFFu), 255.0f);
             }
             packed[cell] = pk;
@@ -737,16 +740,16 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         // ---- coalesced tile write-out
         if (out.image) {
             switch (kp.nch) {
-                case 1: write_image_rows<1>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
-                case 2: write_image_rows<2>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
-                case 3: write_image_rows<3>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
-                default: write_image_rows<4>(packed, out.image, kp.W, grow0, gcol0, nrows, ncols, tid); break;
+                case 1: write_image_rows<1>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
+                case 2: write_image_rows<2>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
+                case 3: write_image_rows<3>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
+                default: write_image_rows<4>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
             }
         }
         if (NW >= 2 && out.count16) {
             for (int it = tid; it < nrows * ncols; it += RED_THREADS) {
                 const int lr = it / ncols, lc = it - lr * ncols;
-                out.count16[(size_t)(grow0 + lr) * kp.W + gcol0 + lc] = (uint16_t)cnt16[(lr << TILE_W_LOG2) + lc];
+                out.count16[(size_t)(orow0 + lr) * kp.W + gcol0 + lc] = (uint16_t)cnt16[(lr << TILE_W_LOG2) + lc];
             }
         }
     }
@@ -858,7 +861,26 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     k.tiles_x = (p->width + TILE_W - 1) >> TILE_W_LOG2;
     k.tiles_y = (p->height + (1 << tile_h_log2) - 1) >> tile_h_log2;
     k.T = k.tiles_x * k.tiles_y;
+    k.oH = p->height;
+    k.orow = 0;
     return k;
+}
+
+int max_tiles() {
+    if (const char *e = getenv("LM_BEV_MAX_TILES")) {      // test knob: forces the row-window loop on small rasters
+        const int v = atoi(e);
+        if (v >= 1 && v <= MAX_TILES) return v;
+    }
+    return MAX_TILES;
+}
+
+// rows per launch so that tiles_x * ceil(rows / TH) <= max_tiles(); 0 if even one tile row is too wide
+int window_rows(const lm_bev_params *p, int tile_h_log2) {
+    const int tiles_x = (p->width + TILE_W - 1) >> TILE_W_LOG2;
+    const int tile_rows = max_tiles() / tiles_x;
+    if (tile_rows < 1) return 0;
+    const long long rows = (long long)tile_rows << tile_h_log2;
+    return rows >= p->height ? p->height : (int)rows;
 }
 
 struct Layout {
@@ -953,9 +975,14 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
         const bool want16 = out->count16_dev != nullptr;
         th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr), want16));
     }
-    const KParams k = make_kparams(p, th);
-    if (algo == LM_ALGO_BINNED && k.T > MAX_TILES)
-        return fail(LM_ERR_UNSUPPORTED, "%d shared-memory tiles > %d: rasterise by row windows", k.T, MAX_TILES);
+    KParams k = make_kparams(p, th);
+    if (algo == LM_ALGO_BINNED) {          // a raster with too many tiles runs as row windows: size for one window
+        const int wrows = window_rows(p, th);
+        if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: %d tiles per tile row > %d", k.tiles_x, max_tiles());
+        lm_bev_params pw = *p;
+        pw.height = wrows;
+        k = make_kparams(&pw, th);
+    }
     Layout L;
     rc = make_layout(p, n_points, algo, k.T, &L);
     if (rc) return rc;
@@ -1014,13 +1041,19 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
         return LM_OK;
     }
 
-    // ---- binned path
+    // ---- binned path (row windows when the raster has more tiles than one launch handles)
     const bool want16 = out->count16_dev != nullptr;
     const int mask = pick_mask(needed_mask(p, want16, out->acc_dev != nullptr), want16);
-    const KParams kp = make_kparams(p, tile_h_log2_for(mask));
-    if (kp.T > MAX_TILES) return fail(LM_ERR_UNSUPPORTED, "%d shared-memory tiles > %d: rasterise by row windows", kp.T, MAX_TILES);
+    const int th = tile_h_log2_for(mask);
+    const int wrows = window_rows(p, th);
+    if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: more than %d tiles per tile row", max_tiles());
+    const int n_win = (p->height + wrows - 1) / wrows;
+    if (n_win > 1 && stages != LM_STAGE_ALL)
+        return fail(LM_ERR_UNSUPPORTED, "stage-split calls need a raster that fits one launch (%d row windows here)", n_win);
+    lm_bev_params pw = *p;
+    pw.height = wrows;
     Layout L;
-    rc = make_layout(p, n_points, algo, kp.T, &L);
+    rc = make_layout(p, n_points, algo, make_kparams(&pw, th).T, &L);
     if (rc) return rc;
     if (workspace_bytes < L.total) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, L.total);
     Ws ws;
@@ -1036,41 +1069,52 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
     ws.acc = nullptr;
     ws.pool_chunks = L.pool_chunks;
 
-    cudaError_t e = cudaSuccess;
-    if (stages & LM_STAGE_BIN) {
-        e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
-        if (e != cudaSuccess) return cuda_fail(e, "memset");
-        if (n_points > 0) {
-            const size_t smem = bin_smem_bytes(kp.T);
-            e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-            // persistent: one wave of resident CTAs, each owning a contiguous range of batches
-            int occ = 1;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_kernel, BIN_THREADS, smem);
-            if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
-            long long grid = (long long)sms * (occ < 1 ? 1 : occ);
-            if (grid > MAX_BIN_CTAS) grid = MAX_BIN_CTAS;
-            const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
-            if (grid > nb) grid = nb;
-            bin_points_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+    for (int win = 0; win < n_win; ++win) {
+        // the window is an integer sub-window of the same global grid: bit-identical to the one-piece raster
+        pw = *p;
+        pw.row0 = p->row0 + win * wrows;
+        pw.height = (win + 1) * wrows <= p->height ? wrows : p->height - win * wrows;
+        KParams kp = make_kparams(&pw, th);
+        kp.oH = p->height;
+        kp.orow = win * wrows;
+        cudaError_t e = cudaSuccess;
+        if (stages & LM_STAGE_BIN) {
+            // stats (first 64 bytes) accumulate over the windows; everything else restarts
+            const size_t skip = win == 0 ? 0 : L.off_ctl;
+            e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
+            if (e != cudaSuccess) return cuda_fail(e, "memset");
+            if (n_points > 0) {
+                const size_t smem = bin_smem_bytes(kp.T);
+                e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
+                // persistent: one wave of resident CTAs, each owning a contiguous range of batches
+                int occ = 1;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_kernel, BIN_THREADS, smem);
+                if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
+                long long grid = (long long)sms * (occ < 1 ? 1 : occ);
+                if (grid > MAX_BIN_CTAS) grid = MAX_BIN_CTAS;
+                const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
+                if (grid > nb) grid = nb;
+                bin_points_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
+            }
         }
+        if (stages & LM_STAGE_INDEX) {
+            scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp.T);
+            if (n_points > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
+        if (!(stages & LM_STAGE_REDUCE)) continue;
+        switch (mask) {
+            case M_MAXI: e = launch_reduce<M_MAXI>(kp, ws, o, sms, st); break;
+            case M_CNT | M_MAXI: e = launch_reduce<M_CNT | M_MAXI>(kp, ws, o, sms, st); break;
+            case M_CNT | M_SUMZ | M_MAXI: e = launch_reduce<M_CNT | M_SUMZ | M_MAXI>(kp, ws, o, sms, st); break;
+            case M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ:
+                e = launch_reduce<M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ>(kp, ws, o, sms, st); break;
+            default: e = launch_reduce<M_ALL>(kp, ws, o, sms, st); break;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles launch");
     }
-    if (stages & LM_STAGE_INDEX) {
-        scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp.T);
-        if (n_points > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
-    }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
-    if (!(stages & LM_STAGE_REDUCE)) return LM_OK;
-    switch (mask) {
-        case M_MAXI: e = launch_reduce<M_MAXI>(kp, ws, o, sms, st); break;
-        case M_CNT | M_MAXI: e = launch_reduce<M_CNT | M_MAXI>(kp, ws, o, sms, st); break;
-        case M_CNT | M_SUMZ | M_MAXI: e = launch_reduce<M_CNT | M_SUMZ | M_MAXI>(kp, ws, o, sms, st); break;
-        case M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ:
-            e = launch_reduce<M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ>(kp, ws, o, sms, st); break;
-        default: e = launch_reduce<M_ALL>(kp, ws, o, sms, st); break;
-    }
-    if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles launch");
     return LM_OK;
 }
 

@@ -56,9 +56,11 @@ def test_workspace_bytes_and_argument_errors(native_lib):
     p = _cabi.make_params(spec)
     assert native_lib.lm_bev_workspace_bytes(C.byref(p), 10, 7, None, C.byref(out)) == -1
     assert native_lib.lm_bev_workspace_bytes(C.byref(p), -1, 0, None, C.byref(out)) == -1
-    # too many shared-memory tiles for one call -> unsupported, shard by row window
-    big = _cabi.make_params(BevSpec(200_000, 200_000))
-    assert native_lib.lm_bev_workspace_bytes(C.byref(big), 10, 0, None, C.byref(out)) == -3
+    # a tall raster runs as row windows inside the call; only a raster too WIDE for one tile row is refused
+    tall = _cabi.make_params(BevSpec(3_000_000, 1152))
+    assert native_lib.lm_bev_workspace_bytes(C.byref(tall), 10, 0, None, C.byref(out)) == 0
+    wide = _cabi.make_params(BevSpec(64, 2_000_000))
+    assert native_lib.lm_bev_workspace_bytes(C.byref(wide), 10, 0, None, C.byref(out)) == -3
     o = _cabi.LmBevOutputs()
     assert native_lib.lm_bev_rasterize(C.byref(p), None, 0, 0, None, 0, C.byref(o), None) == -1  # no outputs
     o.image_dev = 256

@@ -1,0 +1,47 @@
+"""CPU tests of host-side pieces that need no GPU: LAS reader, sidecar transform, split parsing."""
+import json
+
+import numpy as np
+import pytest
+
+from lanemapping_b200 import las, sidecar
+from lanemapping_b200.datasets import read_split, collate_points
+
+
+def test_las_roundtrip_and_header(tmp_path):
+    rng = np.random.default_rng(0)
+    xyz = rng.random((5000, 3)) * [100, 50, 5] + [533000.0, 3380000.0, 20.0]
+    inten = rng.integers(0, 65536, 5000)
+    path = str(tmp_path / "a.las")
+    las.write_las(path, xyz, inten, scale=(0.001, 0.001, 0.001))
+    got, gi, hdr = las.read_las(path)
+    assert hdr.n_points == 5000 and hdr.record_length == 20 and hdr.version == (1, 2)
+    assert np.abs(got - xyz).max() <= 0.0005 + 1e-9 and np.array_equal(gi, inten)
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(ValueError):
+        las.read_las(path)
+
+
+def test_world_local_roundtrip_with_rotation():
+    ang = np.deg2rad(40.0)
+    p = sidecar.PcImgParams("a.las", (5e5, 3e6, 10.0), (3.0, -2.0, 1.0, np.cos(ang / 2), 0, 0, np.sin(ang / 2)),
+                            (0.0, 0.0), (0.05, 0.05), -1.0, 0.05)
+    local = np.array([[1.0, 0.0, 0.5], [10.0, -3.0, 0.1]])
+    world = sidecar.local_to_world(local, p)
+    # a +40 degree rotation about z of (1,0,0), then the two translations
+    assert np.allclose(world[0], [np.cos(ang) + 3.0 + 5e5, np.sin(ang) - 2.0 + 3e6, 0.5 + 1.0 + 10.0])
+    assert np.allclose(sidecar.world_to_local(world, p), local, atol=1e-8)
+    with pytest.raises(ValueError):
+        sidecar.format_sidecar(sidecar.PcImgParams("a", (0, 0), (0,) * 7, (0, 0), (1, 1), 0, 1))
+
+
+def test_split_modes(tmp_path):
+    stems = ["%06d_%04d" % (1, i) for i in range(200)]
+    with open(tmp_path / "s.json", "w") as f:
+        json.dump({"train": stems[:100], "test": stems[100:150], "valid": stems, "single": stems[:1], "pretrain": stems}, f)
+    assert len(read_split(str(tmp_path), "s.json", "train")) == 100
+    assert len(read_split(str(tmp_path), "s.json", "valid")) == 150        # reference caps valid at 150
+    assert read_split(str(tmp_path), "s.json", "all") == stems
+    with pytest.raises(AssertionError):
+        read_split(str(tmp_path), "s.json", "val")                           # reference asserts on unknown modes
