@@ -91,7 +91,7 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
                           img_reso: Tuple[float, float] = (0.05, 0.05), ele_reso: float = 0.05, tile: int = TILE,
                           channels: Sequence[int] = DEFAULT_CHANNELS, count16_dir: Optional[str] = None,
                           pose: Sequence[float] = IDENTITY_POSE, first_index: int = 1, device: str = "cuda",
-                          skip_existing: bool = True) -> List[str]:
+                          skip_existing: bool = True, crop_points_dir: Optional[str] = None) -> List[str]:
     """LAS/NPY cloud -> every non-empty ``tile`` x ``tile`` crop as PNG + sidecar.  Returns the stems."""
     import torch
     from .bev import BevRasterizer, crop_tiles
@@ -140,6 +140,14 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
         r.check_device_errors()
 
     n_c = spec.width // tile
+    crop_of_point = None
+    if crop_points_dir is not None:
+        # which crop every point falls in: the same float32 keys as the rasteriser (spec.py step 1)
+        f32 = np.float32
+        rr = np.floor((pts[:, 0] - f32(spec.bev_img_offset[0])) / f32(img_reso[0]))
+        cc = np.floor((pts[:, 1] - f32(spec.bev_img_offset[1])) / f32(img_reso[1]))
+        ok = (rr >= 0) & (rr < spec.height) & (cc >= 0) & (cc < spec.width)
+        crop_of_point = np.where(ok, (rr // tile) * n_c + (cc // tile), -1).astype(np.int64)
     stems = []
     for k in range(crops.shape[0]):
         if not crops[k].any():
@@ -154,6 +162,9 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
         if crops16 is not None:
             import cv2
             cv2.imwrite(os.path.join(count16_dir, stem + ".png"), crops16[k])
+        if crop_of_point is not None:
+            # packed point records of this crop for the on-the-fly dataset (lanemapping_b200/datasets.py)
+            np.save(os.path.join(crop_points_dir, stem + ".npy"), pts[crop_of_point == k])
         stems.append(stem)
     with open(manifest, "w") as f:
         json.dump({"source": las_filename, "stems": stems, "grid": [spec.height, spec.width],
@@ -168,7 +179,7 @@ def multiprocessing_las_files(las_filenames: Sequence[str], new_tiff_dir: str, n
     processes: CUDA contexts do not survive ``fork``; LAS parsing, PNG encoding and the GPU
     calls all release the GIL."""
     import tqdm
-    for d in (new_tiff_dir, new_param_dir, opts.get("count16_dir")):
+    for d in (new_tiff_dir, new_param_dir, opts.get("count16_dir"), opts.get("crop_points_dir")):
         if d and not os.path.exists(d):
             os.makedirs(d)
     stems: List[str] = []

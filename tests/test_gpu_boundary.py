@@ -77,7 +77,8 @@ def test_offline_converter_writes_reference_compatible_files(bev, tmp_path):
     las_path = str(tmp_path / "181013_road.las")
     las.write_las(las_path, world, inten, offset=(533000.0, 3380000.0, 0.0))
     tiff, param = str(tmp_path / "cropped_tiff"), str(tmp_path / "cropped_tiff_param")
-    stems = multiprocessing_las_files([las_path], tiff, param, num_process=2)
+    cpts = str(tmp_path / "crop_points")
+    stems = multiprocessing_las_files([las_path], tiff, param, num_process=2, crop_points_dir=cpts)
     assert stems == ["181013_0001", "181013_0002"] and all(len(s) == 11 for s in stems)   # 60 m -> 2 crops of 57.6 m
     assert multiprocessing_las_files([las_path], tiff, param, num_process=1) == stems       # resumable: manifest hit
     xyz, inten_rd, hdr = las.read_las(las_path)
@@ -103,6 +104,21 @@ def test_offline_converter_writes_reference_compatible_files(bev, tmp_path):
         assert np.allclose(back[0, :, 0], 533000.0 + k * 57.6 + rows * 0.05, atol=1e-6)
         assert np.allclose(back[0, :, 1], 3380000.0 + 300 * 0.05, atol=1e-6)
         assert np.all(np.abs(back[0, :, 2] - 21.0) <= p.ele_reso + 0.05)
+    # the per-crop point records written for the on-the-fly dataset rasterise to the same crops
+    from lanemapping_b200.pcencoder import BatchProjector
+    crop_pts = [torch.from_numpy(np.load(os.path.join(cpts, s + ".npy"))).cuda() for s in stems]
+    assert sum(len(c) for c in crop_pts) == n
+    geoms = []
+    for s in stems:
+        q = sidecar.read_sidecar(os.path.join(param, s + ".txt"))
+        geoms.append([q.bev_img_offset[0], q.bev_img_offset[1], q.img_reso[0], q.img_reso[1], q.local_min_ele, q.ele_reso])
+    proj = BatchProjector()(crop_pts, torch.tensor(geoms, dtype=torch.float64))
+    for k, s in enumerate(stems):
+        png = np.array(Image.open(os.path.join(tiff, s + ".png")), dtype=np.uint8)
+        # crop 0's own origin is the mosaic origin; crop 1 is re-keyed from a shifted float origin, which
+        # may move points that sit exactly on a cell edge: compare crop 0 exactly, crop 1 within 0.1 % of cells
+        same = (proj[k].cpu().numpy() == O.proj_from_image(png))
+        assert same.all() if k == 0 else same.mean() > 0.999
     man = json.load(open(os.path.join(param, "181013.manifest.json")))
     assert man["stems"] == stems and man["n_points"] == n
 
