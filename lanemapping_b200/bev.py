@@ -19,15 +19,16 @@ OUTPUT_KEYS = ("image", "count16", "proj", "acc")
 
 
 def workspace_bytes(spec: BevSpec, n_points: int, algo: str = "binned",
-                    outputs: Optional[Iterable[str]] = None) -> int:
+                    outputs: Optional[Iterable[str]] = None, acc_band: int = 0) -> int:
     """Device workspace for one call; ``outputs`` (the buffers that will be requested) tightens it."""
     p = _cabi.make_params(spec)
     out = C.c_size_t(0)
     o = None
     if outputs is not None:
         o = _cabi.LmBevOutputs()
-        for k in outputs:                      # only non-NULL-ness matters for sizing
+        for k in outputs:                      # only non-NULL-ness (and the band) matters for sizing
             setattr(o, k + "_dev", 1)
+        o.acc_band = int(acc_band)
     _cabi.check(_cabi.lib().lm_bev_workspace_bytes(C.byref(p), int(n_points), ALGOS[algo],
                                                    C.byref(o) if o is not None else None, C.byref(out)))
     return int(out.value)
@@ -65,8 +66,8 @@ class BevRasterizer:
         self.max_points = int(max_points)
         self._params = _cabi.make_params(spec)
         self._lib = _cabi.lib()
-        self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo, outputs), dtype=torch.uint8,
-                                     device=self.device)
+        self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo, outputs, self.acc_band),
+                                     dtype=torch.uint8, device=self.device)
 
     # -- buffers ----------------------------------------------------------------------------
     def alloc_outputs(self) -> Dict[str, torch.Tensor]:

@@ -163,8 +163,11 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
             import cv2
             cv2.imwrite(os.path.join(count16_dir, stem + ".png"), crops16[k])
         if crop_of_point is not None:
-            # packed point records of this crop for the on-the-fly dataset (lanemapping_b200/datasets.py)
-            np.save(os.path.join(crop_points_dir, stem + ".npy"), pts[crop_of_point == k])
+            # packed point records of this crop for the on-the-fly dataset (lanemapping_b200/datasets.py),
+            # with the MOSAIC origin + the crop's integer window so that re-rasterising is bit-identical
+            geom = np.array([spec.bev_img_offset[0], spec.bev_img_offset[1], img_reso[0], img_reso[1],
+                             spec.local_min_ele, spec.ele_reso, i * tile, j * tile], dtype=np.float64)
+            np.savez(os.path.join(crop_points_dir, stem + ".npz"), points=pts[crop_of_point == k], geom=geom)
         stems.append(stem)
     with open(manifest, "w") as f:
         json.dump({"source": las_filename, "stems": stems, "grid": [spec.height, spec.width],

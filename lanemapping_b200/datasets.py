@@ -4,7 +4,7 @@ The reference's loaders read ``cropped_tiff/<stem>.png`` in forked DataLoader wo
 (reference baseline/datasets/laserlane_proposals.py:73-98; ``workers=12, pin_memory=True``,
 reference baseline/datasets/registry.py:54-59).  CUDA cannot be used there, so the on-the-fly
 path splits the work: this dataset only *loads* each crop's packed point records
-(``<data_root>/crop_points/<stem>.npy`` float32 [N,4] + the sidecar) in the worker, and the
+(``<data_root>/crop_points/<stem>.npz``: float32 [N,4] + raster geometry) in the worker, and the
 rasterisation runs in the main process on the GPU inside the PCENCODER wrapper
 (lanemapping_b200/pcencoder.py), which fills ``sample['proj']``.
 
@@ -57,12 +57,20 @@ class CropPoints(Dataset):
 
     def load_points(self, idx: int) -> Dict[str, torch.Tensor]:
         stem = self.image_stem_list[idx]
-        pts = np.load(osp.join(self.points_path, stem + ".npy"))
+        npz = osp.join(self.points_path, stem + ".npz")
+        if osp.exists(npz):
+            # written by convert_data.rasterize_single_file(crop_points_dir=...): mosaic origin + integer
+            # window of the crop -> the on-the-fly raster is bit-identical to the crop's PNG
+            with np.load(npz) as z:
+                pts, geom = z["points"], torch.from_numpy(z["geom"].astype(np.float64))
+        else:
+            # plain [N,4] records + the crop's own sidecar (its origin is the shifted float origin)
+            pts = np.load(osp.join(self.points_path, stem + ".npy"))
+            p = read_sidecar(osp.join(self.param_path, stem + ".txt"))
+            geom = torch.tensor([p.bev_img_offset[0], p.bev_img_offset[1], p.img_reso[0], p.img_reso[1],
+                                 p.local_min_ele, p.ele_reso, 0.0, 0.0], dtype=torch.float64)
         if pts.ndim != 2 or pts.shape[1] != 4:
-            raise ValueError(f"{stem}.npy: expected [N,4] (x, y, z, intensity)")
-        p = read_sidecar(osp.join(self.param_path, stem + ".txt"))
-        geom = torch.tensor([p.bev_img_offset[0], p.bev_img_offset[1], p.img_reso[0], p.img_reso[1],
-                             p.local_min_ele, p.ele_reso], dtype=torch.float64)
+            raise ValueError(f"{stem}: expected [N,4] (x, y, z, intensity)")
         return {"points": torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float32)), "bev_geom": geom}
 
     def __getitem__(self, idx):

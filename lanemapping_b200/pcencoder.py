@@ -32,8 +32,9 @@ class BatchProjector:
         if geom is None:
             return BevSpec(self.tile, self.tile, img_reso=self.img_reso, ele_reso=self.ele_reso, channels=self.channels)
         g = [float(v) for v in geom]
+        row0, col0 = (int(g[6]), int(g[7])) if len(g) >= 8 else (0, 0)
         return BevSpec(self.tile, self.tile, bev_img_offset=(g[0], g[1]), img_reso=(g[2], g[3]), local_min_ele=g[4],
-                       ele_reso=g[5], channels=self.channels)
+                       ele_reso=g[5], channels=self.channels, row0=row0, col0=col0)
 
     def __call__(self, points: List[torch.Tensor], geoms=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         from .bev import BevRasterizer

@@ -200,3 +200,19 @@ def test_exact_division_exhaustive(bev, native_lib, divisor):
     bad, fast = (int(v) for v in out.cpu())
     assert fast == 104 * 2**24          # dividends with exponent in [2^-40, 2^64), both signs
     assert bad == 0, f"{bad} dividends where the fast division differs from __fdiv_rn for divisor {divisor}"
+
+
+@pytest.mark.parametrize("band", [64, 100])
+def test_banded_raw_accumulators(bev, band):
+    """Halo mode: raw accumulators only on the first/last `band` rows (6-plane kernel on the band tiles,
+    light kernel elsewhere); image everywhere.  Band rows of acc and the whole image must be exact."""
+    spec = BevSpec(900, 700, img_reso=(0.1, 0.1), channels=CFG2_CH, local_min_ele=-2.0)
+    cloud = make_cloud(800_000, spec, seed=41, order="scan")
+    r = bev.BevRasterizer(spec, len(cloud), outputs=["image", "acc"], acc_band=band)
+    out = r(torch.from_numpy(cloud).cuda())
+    torch.cuda.synchronize()
+    r.check_device_errors()
+    acc = O.accumulate(cloud, spec)
+    got = out["acc"].cpu().numpy().view(np.uint32)
+    assert np.array_equal(out["image"].cpu().numpy(), O.finalize(acc, spec)["image"])
+    assert np.array_equal(got[:, :band], acc[:, :band]) and np.array_equal(got[:, -band:], acc[:, -band:])
