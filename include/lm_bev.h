@@ -102,8 +102,10 @@ typedef struct lm_bev_outputs {
     float    *proj_dev;     /* [n_channels][height][width] f32 = u8/255: the loader's   */
                             /* to_tensor(...).float() (laserlane_proposals.py:88-89)    */
     uint32_t *acc_dev;      /* [LM_ACC_PLANES][height][width] raw accumulators          */
-    int32_t   acc_band;     /* acc_dev rows written: <=0 all rows; else only tiles that */
-                            /* intersect rows [0,band) or [height-band,height)          */
+    int32_t   acc_band;     /* <=0: all six planes, all rows.  >0 (halo mode, with another */
+                            /* output requested): only tiles touching rows [0,band) or    */
+                            /* [height-band,height) are written, and only the planes the  */
+                            /* requested channels need are accumulated (others read empty) */
     int32_t   reserved;
 } lm_bev_outputs;
 

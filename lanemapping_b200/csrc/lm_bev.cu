@@ -81,10 +81,8 @@ struct KParams {
 
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
     unsigned int pool_cursor;   // chunks handed out so far (chunk ids are cursor+1: id 0 = none)
-    unsigned int tile_counter;  // reduce_tiles scheduler (all / interior tiles)
-    unsigned int band_counter;  // reduce_tiles scheduler (halo-band tiles)
-    unsigned int n_band;        // entries of band_order
-    unsigned int pad[4];
+    unsigned int tile_counter;  // reduce_tiles scheduler
+    unsigned int pad[6];
 };
 
 struct Ws {                  // device pointers into the caller's workspace
@@ -94,7 +92,6 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t *tile_first;    // [T]
     uint32_t *tile_cursor;   // [T]
     uint32_t *tile_order;    // [T] tiles sorted heaviest first (reduce_tiles schedule)
-    uint32_t *band_order;    // [T] tiles that intersect the halo bands (raw accumulators wanted)
     uint2 *chunk_meta;       // [P] {tile, count}
     uint32_t *chunk_index;   // [P] per-tile chunk lists: id | (count-1) << 23
     uint32_t *pool;          // [P][CHUNK_RECS]
@@ -544,7 +541,6 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
         const uint32_t lvl = 1023u - min(ws.tile_nchunks[t], 1023u);
         const uint32_t pos = atomicAdd(&s_lvl[lvl], 0xFFFFFFFFu) - 1u;      // fill each level's slot range from its end
         ws.tile_order[pos] = (uint32_t)t;
-        if (tile_in_band(kp, t)) ws.band_order[atomicAdd(&ws.ctl->n_band, 1u)] = (uint32_t)t;
     }
 }
 
@@ -613,9 +609,8 @@ __device__ __forceinline__ void accumulate_rec(uint32_t rec, uint32_t *a_cnt, ui
     if (MASK & M_MAXZ) atomicMax(&a_maxz[cell], zq);
 }
 
-// SEL: 0 = every tile, 1 = only halo-band tiles (band_order), 2 = every tile except the band tiles
-template <int MASK, int SEL>
-__global__ void __launch_bounds__(RED_THREADS, popc6(MASK) > 5 ? 1 : RED_MIN_CTAS) reduce_tiles_kernel(KParams kp, Ws ws, Outs out) {
+template <int MASK>
+__global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel(KParams kp, Ws ws, Outs out) {
     constexpr int NW = popc6(MASK);
     extern __shared__ __align__(16) uint32_t acc[];      // [NW][cells]; plane 0/1 reused as packed/count16
     __shared__ int s_tile;
@@ -635,18 +630,19 @@ __global__ void __launch_bounds__(RED_THREADS, popc6(MASK) > 5 ? 1 : RED_MIN_CTA
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_tile = (int)atomicAdd(SEL == 1 ? &ws.ctl->band_counter : &ws.ctl->tile_counter, 1u);
+        if (tid == 0) s_tile = (int)atomicAdd(&ws.ctl->tile_counter, 1u);
         __syncthreads();
-        if (s_tile >= (SEL == 1 ? (int)ws.ctl->n_band : kp.T)) break;
-        const int t = (int)(SEL == 1 ? ws.band_order[s_tile] : ws.tile_order[s_tile]);   // tile_order: heaviest first
-        if (SEL == 2 && tile_in_band(kp, t)) continue;
+        if (s_tile >= kp.T) break;
+        const int t = (int)ws.tile_order[s_tile];               // heaviest tiles first
         const int trow = t / kp.tiles_x, tcol = t - trow * kp.tiles_x;
         const int grow0 = trow << kp.tile_h_log2, gcol0 = tcol << TILE_W_LOG2;
         const int nrows = min(TH, kp.H - grow0), ncols = min(TILE_W, kp.W - gcol0);
         const uint32_t nchunks = ws.tile_nchunks[t];
         const uint32_t *my_index = ws.chunk_index + ws.tile_first[t];
         const int orow0 = kp.orow + grow0;                       // first row of this tile in the output buffers
-        const bool want_raw = out.acc != nullptr;                // band selection happened through SEL
+        // raw planes: everywhere (band <= 0) or only for tiles touching the halo bands.  In band mode
+        // only the planes the requested channels need are accumulated; the others are written as empty.
+        const bool want_raw = out.acc != nullptr && (kp.band <= 0 || tile_in_band(kp, t));
 
         // first chunk of this warp: issue its loads before zeroing so the latency overlaps
         uint32_t c = warp;
@@ -900,7 +896,7 @@ int window_rows(const lm_bev_params *p, int tile_h_log2) {
 }
 
 struct Layout {
-    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, off_band, zero_bytes;
+    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, zero_bytes;
     size_t off_meta, off_index, off_pool, off_acc, total;
     uint32_t pool_chunks;
     int bin_ctas;
@@ -930,7 +926,6 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
     L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
-    L->off_band = o;    o = align_up(o + (size_t)T * 4, 256);
     // full chunks + one open chunk per (CTA, tile) + chunk ids a CTA may abandon in its stash
     const unsigned long long full = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS);
     const unsigned long long chunks = full + full / (STASH / STASH_LOW) +
@@ -949,29 +944,28 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
 
 size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * 4 * (1 + NSLOT); }
 
-template <int MASK, int SEL>
+template <int MASK>
 cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sms, cudaStream_t st) {
     const size_t smem = (size_t)popc6(MASK) * ((size_t)TILE_W << kp.tile_h_log2) * 4;
-    cudaError_t e = cudaFuncSetAttribute(reduce_tiles_kernel<MASK, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(reduce_tiles_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK, SEL>, RED_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK>, RED_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     const int grid = kp.T < sms * occ ? kp.T : sms * occ;
-    reduce_tiles_kernel<MASK, SEL><<<grid, RED_THREADS, smem, st>>>(kp, ws, o);
+    reduce_tiles_kernel<MASK><<<grid, RED_THREADS, smem, st>>>(kp, ws, o);
     return cudaGetLastError();
 }
 
-template <int SEL>
 cudaError_t launch_reduce_mask(int mask, const KParams &kp, const Ws &ws, const Outs &o, int sms, cudaStream_t st) {
     switch (mask) {
-        case M_MAXI: return launch_reduce<M_MAXI, SEL>(kp, ws, o, sms, st);
-        case M_CNT | M_MAXI: return launch_reduce<M_CNT | M_MAXI, SEL>(kp, ws, o, sms, st);
-        case M_CNT | M_SUMZ | M_MAXI: return launch_reduce<M_CNT | M_SUMZ | M_MAXI, SEL>(kp, ws, o, sms, st);
+        case M_MAXI: return launch_reduce<M_MAXI>(kp, ws, o, sms, st);
+        case M_CNT | M_MAXI: return launch_reduce<M_CNT | M_MAXI>(kp, ws, o, sms, st);
+        case M_CNT | M_SUMZ | M_MAXI: return launch_reduce<M_CNT | M_SUMZ | M_MAXI>(kp, ws, o, sms, st);
         case M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ:
-            return launch_reduce<M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ, SEL>(kp, ws, o, sms, st);
-        default: return launch_reduce<M_ALL, SEL>(kp, ws, o, sms, st);
+            return launch_reduce<M_CNT | M_SUMI | M_MAXI | M_MINZ | M_MAXZ>(kp, ws, o, sms, st);
+        default: return launch_reduce<M_ALL>(kp, ws, o, sms, st);
     }
 }
 
@@ -1005,7 +999,6 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
         const bool banded = out->acc_dev != nullptr && out->acc_band > 0 &&
                             (out->image_dev || out->count16_dev || out->proj_dev);
         th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16));
-        if (banded && th > 6) th = 6;
     }
     KParams k = make_kparams(p, th);
     if (algo == LM_ALGO_BINNED) {          // a raster with too many tiles runs as row windows: size for one window
@@ -1075,12 +1068,11 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
 
     // ---- binned path (row windows when the raster has more tiles than one launch handles)
     const bool want16 = out->count16_dev != nullptr;
-    // raw accumulators on halo bands only: the 6-plane kernel runs over the band tiles, the light
-    // kernel over the rest -- both on the light kernel's tile geometry (6 planes of 128 x 64 still fit)
+    // raw accumulators on halo bands only (acc_band > 0): the kernel keeps just the planes the requested
+    // channels need and also emits them raw for the band tiles; acc_band <= 0 accumulates all six planes
     const bool banded = out->acc_dev != nullptr && out->acc_band > 0 && (o.image || o.count16 || o.proj);
     const int mask = pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16);
-    int th = tile_h_log2_for(mask);
-    if (banded && th > 6) th = 6;
+    const int th = tile_h_log2_for(mask);
     const int wrows = window_rows(p, th);
     if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: more than %d tiles per tile row", max_tiles());
     const int n_win = (p->height + wrows - 1) / wrows;
@@ -1099,7 +1091,6 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
     ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
     ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
     ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
-    ws.band_order = reinterpret_cast<uint32_t *>(w + L.off_band);
     ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
     ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
     ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
@@ -1143,15 +1134,7 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
         if (!(stages & LM_STAGE_REDUCE)) continue;
-        if (banded) {
-            e = launch_reduce_mask<1>(M_ALL, kp, ws, o, sms, st);            // band tiles: raw planes + outputs
-            if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles (band) launch");
-            Outs oi = o;
-            oi.acc = nullptr;
-            e = launch_reduce_mask<2>(mask, kp, ws, oi, sms, st);            // everything else
-        } else {
-            e = launch_reduce_mask<0>(mask, kp, ws, o, sms, st);
-        }
+        e = launch_reduce_mask(mask, kp, ws, o, sms, st);
         if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles launch");
     }
     return LM_OK;

@@ -14,8 +14,8 @@ bench number uses clouds from this generator.  Distributions:
   so that the clip is exercised;
 * ~0.5 % of the points fall outside the grid and must be dropped, never clamped.
 
-Two orderings: ``scan`` (along-track monotone with +-1 m jitter: what an MLS
-trajectory produces, spatially coherent) and ``shuffled`` (worst case).
+Two orderings: ``scan`` (acquisition order: road by road, each along-track monotone with
++-1 m jitter -- what MLS trajectories produce, spatially coherent) and ``shuffled`` (worst case).
 """
 from __future__ import annotations
 
@@ -55,15 +55,20 @@ def make_cloud(n_points: int, spec: BevSpec, seed: int = SEED, order: str = "sca
         if m <= 0:
             break
         rng = np.random.default_rng(child)
-        # along-track
+        # along-track; which of the `roads` parallel roads a point belongs to
         if order == "scan":
-            x = (np.arange(lo, hi, dtype=np.float64) + rng.random(m)) * (length / n_points)
+            # acquisition order: the vehicle drives one road after the other, so the cloud is the
+            # concatenation of the roads' scans, each along-track monotone with +-1 m jitter
+            idx = np.arange(lo, hi, dtype=np.float64)
+            road = np.minimum(np.floor(idx * roads / n_points), roads - 1)
+            per_road = n_points / roads
+            x = (idx - road * per_road + rng.random(m)) * (length / per_road)
             x += rng.uniform(-1.0, 1.0, m)
         else:
             x = rng.random(m) * length
+            road = rng.integers(0, roads, m).astype(np.float64)
         x += x_lo
-        # cross-track mixture (each point belongs to one of `roads` parallel roads)
-        centre = y_lo + (rng.integers(0, roads, m) + 0.5) * pitch if roads > 1 else y_lo + 0.5 * width
+        centre = y_lo + (road + 0.5) * pitch
         y = np.where(rng.random(m) < 0.8, rng.normal(centre, 6.0, m), y_lo + rng.random(m) * width)
         # ~0.5 % thrown well outside (either axis)
         outside = rng.random(m) < 0.005
