@@ -121,6 +121,13 @@ class StripRasterizer:
         # raw accumulators are needed on the halo band and on the strip-edge band it merges into
         self.raster = self.backend.make(self.local_spec, max_points, outputs, 2 * halo if self.need_acc else 0)
         self.out = self.raster.alloc_outputs()
+        # pipelined mode (step / flush): two output sets so that the gather of one scene overlaps the
+        # rasterisation of the next one
+        self._outs = [self.out, None]
+        self._mosaics = [None, None]
+        self._gather_done = [None, None]
+        self._comm_stream = None
+        self._step = 0
         W = spec.width
         mk = lambda rows: torch.empty((ACC_PLANES, rows, W), dtype=torch.int32, device=self.device)
         self._send_up = mk(p.top) if p.top else None
@@ -162,6 +169,47 @@ class StripRasterizer:
         if p.bottom:
             self.backend.merge(acc[:, hl - 2 * p.bottom:hl - p.bottom], self._recv_dn)
             self.backend.finalize(self.local_spec, acc, hl - 2 * p.bottom, hl - p.bottom, {"image": out["image"]})
+
+    # -- pipelined steps: rasterise scene k while scene k-1's mosaic is still being gathered -----------
+    def step(self, points: torch.Tensor) -> int:
+        """Enqueue one full scene (rasterise + halo merge on the current stream, mosaic all-gather on a
+        side stream) and return its buffer slot; ``mosaic(slot)`` waits for and returns the result.
+        At most two scenes are in flight: slot k % 2 is reused by scene k + 2."""
+        if self.device.type != "cuda":
+            raise RuntimeError("step() needs CUDA streams; use rasterize() + gather() on CPU back ends")
+        k = self._step % 2
+        self._step += 1
+        main = torch.cuda.current_stream(self.device)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.device)
+        if self._outs[k] is None:
+            self._outs[k] = self.raster.alloc_outputs()
+        if self._gather_done[k] is not None:
+            main.wait_event(self._gather_done[k])          # the strip buffer is free once its gather has run
+        p = self.plan
+        out = self.raster(points, out=self._outs[k])
+        if self.need_acc:
+            self._exchange_and_merge(out)
+        hl = self.local_spec.height
+        strip = out["image"][p.top:hl - p.bottom]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ready)
+            self._mosaics[k] = self.gather(strip)
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        self._gather_done[k] = done
+        return k
+
+    def mosaic(self, slot: int) -> torch.Tensor:
+        torch.cuda.current_stream(self.device).wait_event(self._gather_done[slot])
+        return self._mosaics[slot]
+
+    def flush(self) -> None:
+        for ev in self._gather_done:
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
 
     def _peer(self, r: int) -> int:
         return r if self.group is None else dist.get_global_rank(self.group, r)

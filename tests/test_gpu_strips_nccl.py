@@ -35,8 +35,13 @@ def _worker(rank, world, port, q):
         strip = sr.rasterize(mine)
         mosaic = sr.gather(strip)
         one = BevRasterizer(spec, len(cloud), outputs=("image",))(torch.from_numpy(cloud).cuda())["image"]
+        # pipelined form: three scenes in flight through the two buffer slots
+        slots = [sr.step(mine) for _ in range(3)]
+        piped = sr.mosaic(slots[-1]).clone()
+        sr.flush()
         torch.cuda.synchronize()
-        q.put((rank, bool(torch.equal(mosaic, one)), int(mine.shape[0])))
+        ok = bool(torch.equal(mosaic, one)) and bool(torch.equal(piped, one)) and slots == [0, 1, 0]
+        q.put((rank, ok, int(mine.shape[0])))
     finally:
         dist.destroy_process_group()
 
