@@ -35,7 +35,14 @@ namespace {
 // ------------------------------------------------------------------------------------------
 constexpr int TILE_W_LOG2 = 7;            // shared-memory tile: 128 cols x (128 | 64) rows
 constexpr int TILE_W = 1 << TILE_W_LOG2;
-constexpr int CHUNK_RECS = 512;           // records per pool chunk (2 KB)
+#ifndef LM_CHUNK_LOG2
+#define LM_CHUNK_LOG2 10
+#endif
+constexpr int CHUNK_RECS = 1 << LM_CHUNK_LOG2;   // records per pool chunk (allocation unit of bin_points)
+constexpr int PIECE_RECS = 512;                  // records per work unit of reduce_tiles (2 KB)
+constexpr int HALVES = CHUNK_RECS / PIECE_RECS;  // pieces per chunk
+static_assert(CHUNK_RECS % PIECE_RECS == 0 && HALVES >= 1, "chunk = whole pieces");
+constexpr int IDX_ID_BITS = 23;                  // index entry: piece id | (count-1) << 23
 #ifndef LM_BIN_THREADS
 #define LM_BIN_THREADS 256
 #endif
@@ -43,12 +50,12 @@ constexpr int CHUNK_RECS = 512;           // records per pool chunk (2 KB)
 #define LM_BIN_PPT 4
 #endif
 #ifndef LM_BIN_MIN_CTAS
-#define LM_BIN_MIN_CTAS 3
+#define LM_BIN_MIN_CTAS 4
 #endif
 constexpr int BIN_THREADS = LM_BIN_THREADS;
 constexpr int BIN_PPT = LM_BIN_PPT;       // points per thread per batch
 constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
-constexpr int MAX_BIN_CTAS = 148 * LM_BIN_MIN_CTAS;   // sizing constant of the workspace (B200: 148 SMs)
+constexpr int MAX_BIN_CTAS = 148 * (LM_BIN_MIN_CTAS + 1);   // most bin CTAs ever launched (B200: 148 SMs)
 constexpr int RED_THREADS = 512;
 constexpr int RED_MIN_CTAS = 2;          // shared-memory tiles are sized so that two CTAs fit per SM
 constexpr int MAX_TILES = 9000;           // bin_points keeps 20 B of append state per tile in shared memory
@@ -334,9 +341,10 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
 // ------------------------------------------------------------------------------------------
 // LM_ALGO_BINNED stage 1: bin_points
 // ------------------------------------------------------------------------------------------
+// tile_nchunks counts 512-record PIECES (the reduce kernel's work unit), a chunk holds HALVES of them
 __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_t count, uint32_t tile) {
     ws.chunk_meta[id] = make_uint2(tile, count);
-    atomicAdd(&ws.tile_nchunks[tile], 1u);
+    atomicAdd(&ws.tile_nchunks[tile], (count + PIECE_RECS - 1) / PIECE_RECS);
 }
 
 // Per-CTA append state, all in shared memory:
@@ -348,10 +356,10 @@ __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_
 // serial: two balanced phases (reserve / store) separated by one barrier each.
 // A batch appends at most BIN_BATCH <= 2 * CHUNK records to a tile, i.e. it starts at most two new
 // blocks, so four ring slots can never wrap inside the window that is still being read.
-constexpr int CHUNK_LOG2 = 9;
-static_assert((1 << CHUNK_LOG2) == CHUNK_RECS, "CHUNK_LOG2");
+constexpr int CHUNK_LOG2 = LM_CHUNK_LOG2;
 static_assert(BIN_BATCH <= 2 * CHUNK_RECS, "a batch may start at most two chunk blocks per tile");
-constexpr int NSLOT = 4;
+// a batch that fits one chunk starts at most ONE new block per tile: two ring slots are enough
+constexpr int NSLOT = BIN_BATCH <= CHUNK_RECS ? 2 : 4;
 constexpr int STASH = 128;            // chunk ids fetched per refill
 constexpr int STASH_LOW = 32;         // refill when fewer than this remain (the remainder is abandoned)
 
@@ -551,8 +559,12 @@ __global__ void index_chunks_kernel(Ws ws) {
     for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= last; id += gridDim.x * blockDim.x) {
         const uint2 m = ws.chunk_meta[id];
         if (m.y == 0) continue;                      // abandoned stash id
-        const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], 1u);
-        ws.chunk_index[slot] = id | ((m.y - 1u) << 23);
+        const uint32_t np = (m.y + PIECE_RECS - 1) / PIECE_RECS;               // non-empty pieces of this chunk
+        const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], np);
+        for (uint32_t k = 0; k < np; ++k) {
+            const uint32_t c = min(m.y - k * PIECE_RECS, (uint32_t)PIECE_RECS);
+            ws.chunk_index[slot + k] = (id * HALVES + k) | ((c - 1u) << IDX_ID_BITS);
+        }
     }
 }
 
@@ -597,16 +609,82 @@ __device__ __forceinline__ void write_image_rows(const uint32_t *__restrict__ pa
     }
 }
 
-template <int MASK>
+// count and one sum share a word [count:12 | sum:20] when PACKED: one atomic instead of two (the
+// kernel is bound by shared-memory atomic wavefronts).  sum <= 255 * count < 2^20 while count < 4096;
+// the add that would wrap the count field is seen through the returned old value (*ovf), and the
+// tile is then redone unpacked -- exact for any input.
+constexpr uint32_t PK_SHIFT = 20, PK_SUM_MASK = (1u << PK_SHIFT) - 1u, PK_CNT_MAX = (1u << (32 - PK_SHIFT)) - 1u;
+
+template <int MASK, bool PACKED>
 __device__ __forceinline__ void accumulate_rec(uint32_t rec, uint32_t *a_cnt, uint32_t *a_sumi, uint32_t *a_sumz,
-                                               uint32_t *a_maxi, uint32_t *a_minz, uint32_t *a_maxz) {
+                                               uint32_t *a_maxi, uint32_t *a_minz, uint32_t *a_maxz, uint32_t *ovf) {
     const uint32_t cell = rec >> 16, iq = (rec >> 8) & 0xFFu, zq = rec & 0xFFu;
-    if (MASK & M_CNT) atomicAdd(&a_cnt[cell], 1u);
-    if (MASK & M_SUMI) atomicAdd(&a_sumi[cell], iq);
-    if (MASK & M_SUMZ) atomicAdd(&a_sumz[cell], zq);
+    constexpr bool PACK_Z = PACKED && (MASK & M_SUMZ);            // partner of the count: sum_z if tracked, else sum_i
+    constexpr bool PACK_I = PACKED && !(MASK & M_SUMZ) && (MASK & M_SUMI);
+    if (PACK_Z || PACK_I) {
+        const uint32_t old = atomicAdd(&a_cnt[cell], (1u << PK_SHIFT) | (PACK_Z ? zq : iq));
+        if ((old >> PK_SHIFT) == PK_CNT_MAX) *ovf = 1u;
+    } else if (MASK & M_CNT) {
+        atomicAdd(&a_cnt[cell], 1u);
+    }
+    if ((MASK & M_SUMI) && !PACK_I) atomicAdd(&a_sumi[cell], iq);
+    if ((MASK & M_SUMZ) && !PACK_Z) atomicAdd(&a_sumz[cell], zq);
     if (MASK & M_MAXI) atomicMax(&a_maxi[cell], iq);
     if (MASK & M_MINZ) atomicMax(&a_minz[cell], 256u - zq);
     if (MASK & M_MAXZ) atomicMax(&a_maxz[cell], zq);
+}
+
+// stream one tile's chunks: one chunk per warp and iteration, coalesced uint4 loads with the next
+// chunk's index entry and records fetched while the current ones are reduced
+template <int MASK, bool PACKED>
+__device__ __forceinline__ void stream_tile(const Ws &ws, const uint32_t *my_index, uint32_t nchunks, int warp, int lane,
+                                            uint32_t *a_cnt, uint32_t *a_sumi, uint32_t *a_sumz, uint32_t *a_maxi,
+                                            uint32_t *a_minz, uint32_t *a_maxz, uint32_t *ovf) {
+    constexpr int V = PIECE_RECS / 128;                          // uint4 loads per lane per piece
+    constexpr int NWARPS = RED_THREADS / 32;
+    constexpr uint32_t ID_MASK = (1u << IDX_ID_BITS) - 1u;
+    uint32_t c = warp;
+    uint32_t ent = c < nchunks ? __ldg(my_index + c) : 0u;
+    uint4 v[V];
+    if (c < nchunks) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)(ent & ID_MASK) * PIECE_RECS);
+        const uint32_t cnt = (ent >> IDX_ID_BITS) + 1u;
+#pragma unroll
+        for (int q = 0; q < V; ++q)
+            if ((uint32_t)((q * 32 + lane) * 4) < cnt) v[q] = __ldcs(src + q * 32 + lane);
+    }
+    while (c < nchunks) {
+        const uint32_t cnt = (ent >> IDX_ID_BITS) + 1u;
+        const uint32_t cn = c + NWARPS;
+        const uint32_t ent_next = cn < nchunks ? __ldg(my_index + cn) : 0u;
+        if (cnt == PIECE_RECS) {                 // full piece: no per-record bounds checks
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                accumulate_rec<MASK, PACKED>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                accumulate_rec<MASK, PACKED>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                accumulate_rec<MASK, PACKED>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                accumulate_rec<MASK, PACKED>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const uint32_t i0 = (uint32_t)((q * 32 + lane) * 4);
+                if (i0 + 0 < cnt) accumulate_rec<MASK, PACKED>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                if (i0 + 1 < cnt) accumulate_rec<MASK, PACKED>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                if (i0 + 2 < cnt) accumulate_rec<MASK, PACKED>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                if (i0 + 3 < cnt) accumulate_rec<MASK, PACKED>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+            }
+        }
+        c = cn;
+        ent = ent_next;
+        if (c < nchunks) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)(ent & ID_MASK) * PIECE_RECS);
+            const uint32_t cnt2 = (ent >> IDX_ID_BITS) + 1u;
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                if ((uint32_t)((q * 32 + lane) * 4) < cnt2) v[q] = __ldcs(src + q * 32 + lane);
+        }
+    }
 }
 
 template <int MASK>
@@ -625,8 +703,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
     uint32_t *packed = acc;                                      // plane 0 after the finish step
     uint32_t *cnt16 = acc + cells;                               // plane 1 after the finish step (NW >= 2)
-    constexpr int V = CHUNK_RECS / 128;                          // uint4 loads per lane per chunk
-    constexpr int NWARPS = RED_THREADS / 32;
+    __shared__ uint32_t s_ovf;
 
     for (;;) {
         __syncthreads();
@@ -644,61 +721,29 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         // only the planes the requested channels need are accumulated; the others are written as empty.
         const bool want_raw = out.acc != nullptr && (kp.band <= 0 || tile_in_band(kp, t));
 
-        // first chunk of this warp: issue its loads before zeroing so the latency overlaps
-        uint32_t c = warp;
-        uint32_t ent = c < nchunks ? __ldg(my_index + c) : 0u;
-        uint4 v[V];
-        if (c < nchunks) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)(ent & 0x7FFFFFu) * CHUNK_RECS);
-            const uint32_t cnt = (ent >> 23) + 1u;
-#pragma unroll
-            for (int q = 0; q < V; ++q)
-                if ((uint32_t)((q * 32 + lane) * 4) < cnt) v[q] = __ldcs(src + q * 32 + lane);
-        }
-
         // ---- zero the accumulator tile
-        {
+        auto zero_tile = [&]() {
             uint4 *a4 = reinterpret_cast<uint4 *>(acc);
             const int n4 = NW * cells / 4;
             for (int i = tid; i < n4; i += RED_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-        }
+        };
+        zero_tile();
+        if (tid == 0) s_ovf = 0;
         __syncthreads();
 
-        // ---- stream the tile's chunks: one chunk per warp, integer atomics in shared memory;
-        //      the next chunk's index entry is fetched while the current one is reduced
-        while (c < nchunks) {
-            const uint32_t cnt = (ent >> 23) + 1u;
-            const uint32_t cn = c + NWARPS;
-            const uint32_t ent_next = cn < nchunks ? __ldg(my_index + cn) : 0u;
-            if (cnt == CHUNK_RECS) {                 // full chunk: no per-record bounds checks
-#pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    accumulate_rec<MASK>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                    accumulate_rec<MASK>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                    accumulate_rec<MASK>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                    accumulate_rec<MASK>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    const uint32_t i0 = (uint32_t)((q * 32 + lane) * 4);
-                    if (i0 + 0 < cnt) accumulate_rec<MASK>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                    if (i0 + 1 < cnt) accumulate_rec<MASK>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                    if (i0 + 2 < cnt) accumulate_rec<MASK>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                    if (i0 + 3 < cnt) accumulate_rec<MASK>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-                }
-            }
-            c = cn;
-            ent = ent_next;
-            if (c < nchunks) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(ws.pool + (size_t)(ent & 0x7FFFFFu) * CHUNK_RECS);
-                const uint32_t cnt2 = (ent >> 23) + 1u;
-#pragma unroll
-                for (int q = 0; q < V; ++q)
-                    if ((uint32_t)((q * 32 + lane) * 4) < cnt2) v[q] = __ldcs(src + q * 32 + lane);
-            }
-        }
+        // ---- stream the tile's chunks with integer atomics in shared memory; count+sum packed in one
+        //      word when possible, redone unpacked if a cell's count field overflowed
+        constexpr bool CAN_PACK = (MASK & M_CNT) && (MASK & (M_SUMZ | M_SUMI));
+        stream_tile<MASK, CAN_PACK>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, &s_ovf);
         __syncthreads();
+        const bool packed_ok = CAN_PACK && s_ovf == 0;
+        if (CAN_PACK && !packed_ok) {
+            __syncthreads();                     // everybody has read s_ovf
+            zero_tile();
+            __syncthreads();
+            stream_tile<MASK, false>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, &s_ovf);
+            __syncthreads();
+        }
 
         // ---- finish: raw planes out (halo tiles), then channels packed in place
         const size_t gcells = (size_t)kp.oH * kp.W;
@@ -706,9 +751,13 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         bool overflow = false;
         for (int cell = tid; cell < cells; cell += RED_THREADS) {
             const int lr = cell >> TILE_W_LOG2, lc = cell & (TILE_W - 1);
-            const uint32_t cnt = (MASK & M_CNT) ? a_cnt[cell] : 0u;
-            const uint32_t si = (MASK & M_SUMI) ? a_sumi[cell] : 0u;
-            const uint32_t sz = (MASK & M_SUMZ) ? a_sumz[cell] : 0u;
+            uint32_t cnt = (MASK & M_CNT) ? a_cnt[cell] : 0u;
+            uint32_t si = (MASK & M_SUMI) ? a_sumi[cell] : 0u;
+            uint32_t sz = (MASK & M_SUMZ) ? a_sumz[cell] : 0u;
+            if (packed_ok) {                                     // unpack [count:12 | sum:20]
+                if (MASK & M_SUMZ) sz = cnt & PK_SUM_MASK; else si = cnt & PK_SUM_MASK;
+                cnt >>= PK_SHIFT;
+            }
             const uint32_t mi = (MASK & M_MAXI) ? a_maxi[cell] : 0u;
             const uint32_t nzr = (MASK & M_MINZ) ? a_minz[cell] : 0u;
             const uint32_t xz = (MASK & M_MAXZ) ? a_maxz[cell] : 0u;
@@ -878,6 +927,18 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     return k;
 }
 
+size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * 4 * (1 + NSLOT); }
+
+// upper bound of the bin_points grid for T tiles (shared memory limits the CTAs per SM); the record
+// pool reserves one open chunk per (CTA, tile), so the workspace size and the launch both use it
+int bin_ctas_bound(int T) {
+    const size_t per_sm = 227 * 1024;
+    size_t occ = per_sm / (bin_smem_bytes(T) + 1024);
+    if (occ < 1) occ = 1;
+    if (occ > (size_t)LM_BIN_MIN_CTAS + 1) occ = LM_BIN_MIN_CTAS + 1;
+    return 148 * (int)occ;
+}
+
 int max_tiles() {
     if (const char *e = getenv("LM_BEV_MAX_TILES")) {      // test knob: forces the row-window loop on small rasters
         const int v = atoi(e);
@@ -929,20 +990,18 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     // full chunks + one open chunk per (CTA, tile) + chunk ids a CTA may abandon in its stash
     const unsigned long long full = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS);
     const unsigned long long chunks = full + full / (STASH / STASH_LOW) +
-                                      (unsigned long long)MAX_BIN_CTAS * ((unsigned long long)T + 2 * STASH) + 2ull;
-    if (chunks >= (1ull << 23))     // chunk ids are 23-bit (index entries), record indices 32-bit (2^23 * 512 = 2^32)
+                                      (unsigned long long)bin_ctas_bound(T) * ((unsigned long long)T + 2 * STASH) + 2ull;
+    if (chunks * HALVES >= (1ull << IDX_ID_BITS))     // piece ids share a word with the count; record indices are 32-bit
         return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^23 chunks: shard the call (fewer points or a smaller row window)");
     L->pool_chunks = (uint32_t)chunks;
     // the side table is zeroed too: count == 0 marks chunk ids that were handed out but never used
     L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
     L->zero_bytes = o;
-    L->off_index = o; o = align_up(o + (size_t)chunks * 4, 256);
+    L->off_index = o; o = align_up(o + (size_t)chunks * HALVES * 4, 256);
     L->off_pool = o;  o = align_up(o + (size_t)chunks * CHUNK_RECS * 4, 256);
     L->total = o;
     return LM_OK;
 }
-
-size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * 4 * (1 + NSLOT); }
 
 template <int MASK>
 cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sms, cudaStream_t st) {
@@ -1121,7 +1180,7 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_kernel, BIN_THREADS, smem);
                 if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
                 long long grid = (long long)sms * (occ < 1 ? 1 : occ);
-                if (grid > MAX_BIN_CTAS) grid = MAX_BIN_CTAS;
+                if (grid > bin_ctas_bound(kp.T)) grid = bin_ctas_bound(kp.T);
                 const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
                 if (grid > nb) grid = nb;
                 bin_points_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);

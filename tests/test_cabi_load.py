@@ -38,7 +38,7 @@ def test_workspace_bytes_and_argument_errors(native_lib):
     out = C.c_size_t(0)
     assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_BINNED, None, C.byref(out)) == 0
     binned = out.value
-    assert 4e8 < binned < 8e9 and binned % 256 == 0       # N*4 B of records + chunk slack (upper bound)
+    assert 4e8 < binned < 12e9 and binned % 256 == 0      # N*4 B of records + open-chunk slack (upper bound)
     o = _cabi.LmBevOutputs()
     o.image_dev = 1
     assert native_lib.lm_bev_workspace_bytes(C.byref(p), 100_000_000, _cabi.ALGO_BINNED, C.byref(o), C.byref(out)) == 0
