@@ -141,6 +141,14 @@ __device__ __forceinline__ float div_const(float a, float c, float rc) {
     const float r = __fmaf_rn(-q0, c, a);
     return __fmaf_rn(r, rc, q0);
 }
+// the same three operations on two independent lanes at once (Blackwell FMUL2 / FFMA2: packed
+// binary32, each lane rounds exactly like the scalar instruction)
+__device__ __forceinline__ float2 div_const2(float2 a, float2 c, float2 rc) {
+    const float2 q0 = __fmul2_rn(a, rc);
+    const float2 r = __ffma2_rn(make_float2(-q0.x, -q0.y), c, a);
+    return __ffma2_rn(r, rc, q0);
+}
+
 // the dividends the fast path accepts: finite magnitudes in [2^-40, 2^64)
 __device__ __forceinline__ bool div_fast_ok(float a) { return fabsf(a) >= 0x1p-40f && fabsf(a) < 0x1p64f; }
 
@@ -357,6 +365,7 @@ __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_
 // A batch appends at most BIN_BATCH <= 2 * CHUNK records to a tile, i.e. it starts at most two new
 // blocks, so four ring slots can never wrap inside the window that is still being read.
 constexpr int CHUNK_LOG2 = LM_CHUNK_LOG2;
+static_assert(BIN_PPT % 2 == 0, "z quotients are computed two points at a time");
 static_assert(BIN_BATCH <= 2 * CHUNK_RECS, "a batch may start at most two chunk blocks per tile");
 // a batch that fits one chunk starts at most ONE new block per tile: two ring slots are enough
 constexpr int NSLOT = BIN_BATCH <= CHUNK_RECS ? 2 : 4;
@@ -368,9 +377,12 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = kp.T;
     // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u32
-    const uint32_t sm_stage = smem_u32(smem_raw);
-    const uint32_t sm_pos = sm_stage + 2u * BIN_BATCH * 16u;
-    const uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
+    uint32_t sm_stage = smem_u32(smem_raw);
+    uint32_t sm_pos = sm_stage + 2u * BIN_BATCH * 16u;
+    uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
+    // keep the three bases in registers: without this the compiler re-derives them (window base +
+    // offsets, ~5 instructions) at every use because they are cheap to rematerialise
+    asm volatile("" : "+r"(sm_stage), "+r"(sm_pos), "+r"(sm_slot));
     __shared__ uint32_t s_stash[2][2];                                       // [which]{next id, end id}
     __shared__ uint32_t s_active;                                            // which stash phase 1 draws from
     __shared__ __align__(8) uint64_t s_bar[2];                               // TMA completion barriers
@@ -408,7 +420,11 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             p[j] = lds_f4(my_stage + (uint32_t)j * (BIN_THREADS * 16u));
-            if ((uint32_t)(j * BIN_THREADS + tid) >= npts) p[j].x = __int_as_float(0x7fc00000);   // NaN x: dropped
+        }
+        if (npts < (uint32_t)BIN_BATCH) {                        // only the very last batch of the cloud
+#pragma unroll
+            for (int j = 0; j < BIN_PPT; ++j)
+                if ((uint32_t)(j * BIN_THREADS + tid) >= npts) p[j].x = __int_as_float(0x7fc00000);   // NaN x: dropped
         }
 
         uint32_t rec[BIN_PPT], tl[BIN_PPT], ps[BIN_PPT];
@@ -416,10 +432,35 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
             int r[BIN_PPT], c[BIN_PPT];
             uint32_t iq[BIN_PPT], zq[BIN_PPT];
             bool ok[BIN_PPT];
+            // exact divisions, two lanes per instruction: (x, y) of one point, z of two points
+            float2 qxy[BIN_PPT];
+            float qz[BIN_PPT];
             float lo = 0x1p100f, hi = 0.0f;
+            const float2 noff = make_float2(-kp.off0, -kp.off1), reso2 = make_float2(kp.reso0, kp.reso1),
+                         rr2 = make_float2(kp.rreso0, kp.rreso1);
+            const float2 nzmin2 = make_float2(-kp.zmin, -kp.zmin), zreso2 = make_float2(kp.zreso, kp.zreso),
+                         rz2 = make_float2(kp.rzreso, kp.rzreso);
 #pragma unroll
-            for (int j = 0; j < BIN_PPT; ++j) ok[j] = quantise_fast(p[j], kp, r[j], c[j], iq[j], zq[j], lo, hi);
-            if (!(kp.fast_div && fast_range_ok(lo, hi))) {      // rare: 0, denormal-scale, huge, inf or all-NaN dividends
+            for (int j = 0; j < BIN_PPT; ++j) {
+                const float2 d = __fadd2_rn(make_float2(p[j].x, p[j].y), noff);          // x - off0, y - off1
+                lo = fminf(lo, fminf(fabsf(d.x), fabsf(d.y)));
+                hi = fmaxf(hi, fmaxf(fabsf(d.x), fabsf(d.y)));
+                qxy[j] = div_const2(d, reso2, rr2);
+            }
+#pragma unroll
+            for (int j = 0; j < BIN_PPT; j += 2) {
+                const float2 d = __fadd2_rn(make_float2(p[j].z, p[j + 1].z), nzmin2);    // z - local_min_ele
+                lo = fminf(lo, fminf(fabsf(d.x), fabsf(d.y)));
+                hi = fmaxf(hi, fmaxf(fabsf(d.x), fabsf(d.y)));
+                const float2 q = div_const2(d, zreso2, rz2);
+                qz[j] = q.x;
+                qz[j + 1] = q.y;
+            }
+            if (kp.fast_div && fast_range_ok(lo, hi)) {
+#pragma unroll
+                for (int j = 0; j < BIN_PPT; ++j)
+                    ok[j] = keys_from_quotients(qxy[j].x, qxy[j].y, qz[j], p[j].w, kp, r[j], c[j], iq[j], zq[j]);
+            } else {                                            // rare: 0, denormal-scale, huge, inf or all-NaN dividends
 #pragma unroll
                 for (int j = 0; j < BIN_PPT; ++j) ok[j] = quantise_ieee(p[j], kp, r[j], c[j], iq[j], zq[j]);
             }
@@ -432,10 +473,12 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
             }
         }
         // ---- phase 1: reserve.  The first record of a chunk block allocates the block's chunk.
+        uint32_t sa[BIN_PPT];                                    // shared address of the point's ring slot
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
                 ps[j] = atoms_add(sm_pos + 4u * tl[j], 1u);
+                sa[j] = sm_slot + (4u * NSLOT) * tl[j] + ((ps[j] >> (CHUNK_LOG2 - 2)) & (4u * (NSLOT - 1)));   // ring slot of its block
                 if ((ps[j] & (CHUNK_RECS - 1)) == 0) {
                     uint32_t id = atomicAdd(&s_stash[act][0], 1u);
                     if (id >= s_stash[act][1]) id = atomicAdd(&ws.ctl->pool_cursor, 1u) + 1u;     // stash dry: go global
@@ -443,7 +486,7 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
                         atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
                         id = 0;                                  // chunk 0 is a scratch chunk nobody reads
                     }
-                    sts_u32(sm_slot + 4u * (tl[j] * NSLOT + ((ps[j] >> CHUNK_LOG2) & (NSLOT - 1))), id);
+                    sts_u32(sa[j], id);
                 }
             }
         }
@@ -463,7 +506,7 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
         uint32_t cid[BIN_PPT];
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j)
-            cid[j] = tl[j] != INVALID_U32 ? lds_u32(sm_slot + 4u * (tl[j] * NSLOT + ((ps[j] >> CHUNK_LOG2) & (NSLOT - 1)))) : 0u;
+            cid[j] = tl[j] != INVALID_U32 ? lds_u32(sa[j]) : 0u;
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
@@ -826,7 +869,11 @@ __global__ void selftest_div_kernel(float c, float rc, unsigned long long *out) 
         const float a = __uint_as_float((uint32_t)i);
         if (!div_fast_ok(a)) continue;
         ++fast;
-        if (__float_as_uint(div_const(a, c, rc)) != __float_as_uint(__fdiv_rn(a, c))) ++bad;
+        const uint32_t want = __float_as_uint(__fdiv_rn(a, c));
+        if (__float_as_uint(div_const(a, c, rc)) != want) ++bad;
+        // the packed form the bin kernel uses: this dividend in lane 0, its negation in lane 1
+        const float2 q2 = div_const2(make_float2(a, -a), make_float2(c, c), make_float2(rc, rc));
+        if (__float_as_uint(q2.x) != want || __float_as_uint(q2.y) != (want ^ 0x80000000u)) ++bad;
     }
     for (int o = 16; o; o >>= 1) {
         bad += __shfl_xor_sync(0xffffffffu, bad, o);
