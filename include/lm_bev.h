@@ -167,6 +167,12 @@ int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, i
  * 0), out2_dev[1] = dividends covered by the fast path (the rest take __fdiv_rn itself).     */
 int lm_bev_selftest_div(float divisor, unsigned long long *out2_dev, void *stream);
 
+/* Self-test of the reduce kernel's mean: (sum + count/2) / count is computed with a float
+ * reciprocal when count <= 4095.  Checks it against the integer division for every count in
+ * [1, 4095] and every sum in [0, 255*count]: out2_dev[0] = mismatches (must be 0),
+ * out2_dev[1] = pairs checked.                                                              */
+int lm_bev_selftest_mean(unsigned long long *out2_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -614,41 +614,31 @@ __global__ void index_chunks_kernel(Ws ws) {
 // ------------------------------------------------------------------------------------------
 // stage 3: reduce_tiles
 // ------------------------------------------------------------------------------------------
+// (sum + count/2) / count for count in [1, 4095], sum <= 255 * count, without an integer division:
+// the float estimate is off by < 4.6e-5 absolute (quotient <= 255.5, relative error < 1.8e-7) while
+// a non-integer true quotient is >= 1/4095 = 2.4e-4 away from the integers, so adding 2^-13
+// before truncating lands on the exact floor.  lm_bev_selftest_mean checks every (count, sum).
+__device__ __forceinline__ uint32_t mean_small(uint32_t sum, uint32_t cnt) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)cnt));
+    return (uint32_t)__fmaf_rn((float)(sum + (cnt >> 1)), r, 0x1p-13f);
+}
+
+// four finished pixels (C bytes each, little end first) -> the C 32-bit words they occupy in the image
 template <int C>
-__device__ __forceinline__ void write_image_rows(const uint32_t *__restrict__ packed, uint8_t *image, int W,
-                                                 int grow0, int gcol0, int nrows, int ncols, int tid) {
-    // tile row = ncols*C contiguous bytes; each thread emits one aligned 32-bit word when possible
-    const int bytes = ncols * C;
-    const size_t row_stride = (size_t)W * C;
-    uint8_t *base = image + ((size_t)grow0 * W + gcol0) * C;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 3) == 0) && ((row_stride & 3) == 0);
-    if (aligned) {
-        const int words = bytes >> 2;
-        for (int it = tid; it < nrows * words; it += RED_THREADS) {
-            const int lr = it / words, w = it - lr * words;
-            uint32_t v = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int bi = 4 * w + e;
-                const int cell = bi / C, ch = bi - cell * C;
-                v |= ((packed[(lr << TILE_W_LOG2) + cell] >> (8 * ch)) & 0xFFu) << (8 * e);
-            }
-            *reinterpret_cast<uint32_t *>(base + lr * row_stride + 4 * w) = v;
-        }
-        const int tail = bytes & 3;
-        if (tail) {
-            for (int it = tid; it < nrows * tail; it += RED_THREADS) {
-                const int lr = it / tail, bi = (bytes & ~3) + (it - lr * tail);
-                const int cell = bi / C, ch = bi - cell * C;
-                base[lr * row_stride + bi] = (uint8_t)(packed[(lr << TILE_W_LOG2) + cell] >> (8 * ch));
-            }
-        }
+__device__ __forceinline__ void store_pixels4(uint8_t *dst, const uint32_t pk[4]) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(dst);
+    if (C == 1) {
+        w[0] = (pk[0] & 0xFFu) | ((pk[1] & 0xFFu) << 8) | ((pk[2] & 0xFFu) << 16) | (pk[3] << 24);
+    } else if (C == 2) {
+        w[0] = (pk[0] & 0xFFFFu) | (pk[1] << 16);
+        w[1] = (pk[2] & 0xFFFFu) | (pk[3] << 16);
+    } else if (C == 3) {
+        w[0] = (pk[0] & 0xFFFFFFu) | (pk[1] << 24);
+        w[1] = ((pk[1] >> 8) & 0xFFFFu) | (pk[2] << 16);
+        w[2] = ((pk[2] >> 16) & 0xFFu) | (pk[3] << 8);
     } else {
-        for (int it = tid; it < nrows * bytes; it += RED_THREADS) {
-            const int lr = it / bytes, bi = it - lr * bytes;
-            const int cell = bi / C, ch = bi - cell * C;
-            base[lr * row_stride + bi] = (uint8_t)(packed[(lr << TILE_W_LOG2) + cell] >> (8 * ch));
-        }
+        w[0] = pk[0]; w[1] = pk[1]; w[2] = pk[2]; w[3] = pk[3];
     }
 }
 
@@ -744,9 +734,14 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     uint32_t *a_maxi = acc + plane_of(MASK, M_MAXI) * cells;
     uint32_t *a_minz = acc + plane_of(MASK, M_MINZ) * cells;   // holds max(256 - zq): 0 = empty
     uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
-    uint32_t *packed = acc;                                      // plane 0 after the finish step
-    uint32_t *cnt16 = acc + cells;                               // plane 1 after the finish step (NW >= 2)
     __shared__ uint32_t s_ovf;
+    auto zero_tile = [&]() {
+        uint4 *a4 = reinterpret_cast<uint4 *>(acc);
+        const int n4 = NW * cells / 4;
+        for (int i = tid; i < n4; i += RED_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
+    };
+    zero_tile();            // the finish pass of every tile leaves the planes zeroed for the next one
+    if (tid == 0) s_ovf = 0;
 
     for (;;) {
         __syncthreads();
@@ -764,16 +759,6 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         // only the planes the requested channels need are accumulated; the others are written as empty.
         const bool want_raw = out.acc != nullptr && (kp.band <= 0 || tile_in_band(kp, t));
 
-        // ---- zero the accumulator tile
-        auto zero_tile = [&]() {
-            uint4 *a4 = reinterpret_cast<uint4 *>(acc);
-            const int n4 = NW * cells / 4;
-            for (int i = tid; i < n4; i += RED_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
-        };
-        zero_tile();
-        if (tid == 0) s_ovf = 0;
-        __syncthreads();
-
         // ---- stream the tile's chunks with integer atomics in shared memory; count+sum packed in one
         //      word when possible, redone unpacked if a cell's count field overflowed
         constexpr bool CAN_PACK = (MASK & M_CNT) && (MASK & (M_SUMZ | M_SUMI));
@@ -783,78 +768,135 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         if (CAN_PACK && !packed_ok) {
             __syncthreads();                     // everybody has read s_ovf
             zero_tile();
+            if (tid == 0) s_ovf = 0;
             __syncthreads();
             stream_tile<MASK, false>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, &s_ovf);
             __syncthreads();
         }
 
-        // ---- finish: raw planes out (halo tiles), then channels packed in place
+        // ---- finish + write-out in one pass: every thread takes 4 neighbouring cells of a row (a warp
+        //      covers a whole 128-cell tile row), derives the channels, assembles the output words in
+        //      registers and stores them directly; the planes are zeroed for the next tile on the way
         const size_t gcells = (size_t)kp.oH * kp.W;
         const int nch = kp.nch, ch0 = kp.ch[0], ch1 = kp.ch[1], ch2 = kp.ch[2], ch3 = kp.ch[3];
+        const size_t row_bytes = (size_t)kp.W * nch;
+        const bool full_w = ncols == TILE_W;
+        const bool img_fast = full_w && (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(out.image) & 3) == 0;
+        const bool c16_fast = full_w && (kp.W & 1) == 0 && (reinterpret_cast<uintptr_t>(out.count16) & 3) == 0;
         bool overflow = false;
-        for (int cell = tid; cell < cells; cell += RED_THREADS) {
-            const int lr = cell >> TILE_W_LOG2, lc = cell & (TILE_W - 1);
-            uint32_t cnt = (MASK & M_CNT) ? a_cnt[cell] : 0u;
-            uint32_t si = (MASK & M_SUMI) ? a_sumi[cell] : 0u;
-            uint32_t sz = (MASK & M_SUMZ) ? a_sumz[cell] : 0u;
-            if (packed_ok) {                                     // unpack [count:12 | sum:20]
-                if (MASK & M_SUMZ) sz = cnt & PK_SUM_MASK; else si = cnt & PK_SUM_MASK;
-                cnt >>= PK_SHIFT;
+        for (int g = tid; g < cells / 4; g += RED_THREADS) {
+            const int lr = g >> (TILE_W_LOG2 - 2), lc0 = (g & (TILE_W / 4 - 1)) << 2;
+            const int cell0 = (lr << TILE_W_LOG2) + lc0;
+            const uint4 z4 = make_uint4(0, 0, 0, 0);
+            uint4 vc = z4, vsi = z4, vsz = z4, vmi = z4, vnz = z4, vxz = z4;
+            if (MASK & M_CNT) { vc = *reinterpret_cast<uint4 *>(a_cnt + cell0); *reinterpret_cast<uint4 *>(a_cnt + cell0) = z4; }
+            if (MASK & M_SUMI) { vsi = *reinterpret_cast<uint4 *>(a_sumi + cell0); *reinterpret_cast<uint4 *>(a_sumi + cell0) = z4; }
+            if (MASK & M_SUMZ) { vsz = *reinterpret_cast<uint4 *>(a_sumz + cell0); *reinterpret_cast<uint4 *>(a_sumz + cell0) = z4; }
+            if (MASK & M_MAXI) { vmi = *reinterpret_cast<uint4 *>(a_maxi + cell0); *reinterpret_cast<uint4 *>(a_maxi + cell0) = z4; }
+            if (MASK & M_MINZ) { vnz = *reinterpret_cast<uint4 *>(a_minz + cell0); *reinterpret_cast<uint4 *>(a_minz + cell0) = z4; }
+            if (MASK & M_MAXZ) { vxz = *reinterpret_cast<uint4 *>(a_maxz + cell0); *reinterpret_cast<uint4 *>(a_maxz + cell0) = z4; }
+            if (lr >= nrows) continue;                           // rows below the raster: only zeroed
+            const uint32_t c4[4] = {vc.x, vc.y, vc.z, vc.w}, si4[4] = {vsi.x, vsi.y, vsi.z, vsi.w};
+            const uint32_t sz4[4] = {vsz.x, vsz.y, vsz.z, vsz.w}, mi4[4] = {vmi.x, vmi.y, vmi.z, vmi.w};
+            const uint32_t nz4[4] = {vnz.x, vnz.y, vnz.z, vnz.w}, xz4[4] = {vxz.x, vxz.y, vxz.z, vxz.w};
+            uint32_t pk[4], k16[4];
+            const size_t grow = (size_t)(orow0 + lr) * kp.W + gcol0 + lc0;      // first of the 4 cells in the outputs
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t cnt = c4[e], si = si4[e], sz = sz4[e];
+                if (packed_ok) {                                 // unpack [count:12 | sum:20]
+                    if (MASK & M_SUMZ) sz = cnt & PK_SUM_MASK; else si = cnt & PK_SUM_MASK;
+                    cnt >>= PK_SHIFT;
+                }
+                const uint32_t mi = mi4[e], nzr = nz4[e], xz = xz4[e];
+                const uint32_t nz = nzr ? 256u - nzr : 0u;      // 0 for an empty cell, with or without a count plane
+                overflow |= cnt >= (1u << 24);
+                if (want_raw && lc0 + e < ncols) {
+                    out.acc[LM_ACC_COUNT * gcells + grow + e] = cnt;
+                    out.acc[LM_ACC_SUM_I * gcells + grow + e] = si;
+                    out.acc[LM_ACC_SUM_Z * gcells + grow + e] = sz;
+                    out.acc[LM_ACC_MAX_I * gcells + grow + e] = mi;
+                    out.acc[LM_ACC_MIN_Z * gcells + grow + e] = nzr ? nz : INVALID_U32;
+                    out.acc[LM_ACC_MAX_Z * gcells + grow + e] = xz;
+                }
+                // every candidate channel once, then a select per output byte
+                uint32_t mean_i = 0, mean_z = 0;
+                if (cnt) {
+                    if (packed_ok) {                             // count <= 4095: exact float-reciprocal mean
+                        if (MASK & M_SUMI) mean_i = mean_small(si, cnt);
+                        if (MASK & M_SUMZ) mean_z = mean_small(sz, cnt);
+                    } else {                                     // sums stay < 2^32 while count < 2^24
+                        if (MASK & M_SUMI) mean_i = (si + (cnt >> 1)) / cnt;
+                        if (MASK & M_SUMZ) mean_z = (sz + (cnt >> 1)) / cnt;
+                    }
+                }
+                const uint32_t dens = cnt < 255u ? cnt : 255u;
+                auto pick = [&](int ch) -> uint32_t {
+                    return ch == LM_CH_MAX_I ? mi : ch == LM_CH_MEAN_I ? mean_i : ch == LM_CH_MIN_Z ? nz
+                         : ch == LM_CH_MAX_Z ? xz : ch == LM_CH_MEAN_Z ? mean_z : dens;
+                };
+                uint32_t v = pick(ch0);
+                if (nch > 1) v |= pick(ch1) << 8;
+                if (nch > 2) v |= pick(ch2) << 16;
+                if (nch > 3) v |= pick(ch3) << 24;
+                pk[e] = v;
+                k16[e] = cnt < 65535u ? cnt : 65535u;
             }
-            const uint32_t mi = (MASK & M_MAXI) ? a_maxi[cell] : 0u;
-            const uint32_t nzr = (MASK & M_MINZ) ? a_minz[cell] : 0u;
-            const uint32_t xz = (MASK & M_MAXZ) ? a_maxz[cell] : 0u;
-            const uint32_t nz = nzr ? 256u - nzr : 0u;          // 0 for an empty cell, with or without a count plane
-            overflow |= cnt >= (1u << 24);
-            const bool inside = lr < nrows && lc < ncols;
-            if (want_raw && inside) {
-                const size_t g = (size_t)(orow0 + lr) * kp.W + gcol0 + lc;
-                out.acc[LM_ACC_COUNT * gcells + g] = cnt;
-                out.acc[LM_ACC_SUM_I * gcells + g] = si;
-                out.acc[LM_ACC_SUM_Z * gcells + g] = sz;
-                out.acc[LM_ACC_MAX_I * gcells + g] = mi;
-                out.acc[LM_ACC_MIN_Z * gcells + g] = nzr ? nz : INVALID_U32;
-                out.acc[LM_ACC_MAX_Z * gcells + g] = xz;
+            if (out.image) {
+                uint8_t *dst = out.image + grow * nch;
+                if (img_fast) {
+                    switch (nch) {
+                        case 1: store_pixels4<1>(dst, pk); break;
+                        case 2: store_pixels4<2>(dst, pk); break;
+                        case 3: store_pixels4<3>(dst, pk); break;
+                        default: store_pixels4<4>(dst, pk); break;
+                    }
+                } else {
+                    for (int e = 0; e < 4; ++e)
+                        if (lc0 + e < ncols)
+                            for (int c = 0; c < nch; ++c) dst[e * nch + c] = (uint8_t)(pk[e] >> (8 * c));
+                }
             }
-            // every candidate channel once (sums stay < 2^32 while cnt < 2^24), then a select per output byte
-            const uint32_t half = cnt >> 1, div = cnt ? cnt : 1u;
-            const uint32_t mean_i = (MASK & M_SUMI) ? (si + half) / div : 0u;
-            const uint32_t mean_z = (MASK & M_SUMZ) ? (sz + half) / div : 0u;
-            const uint32_t dens = cnt < 255u ? cnt : 255u;
-            auto pick = [&](int ch) -> uint32_t {
-                return ch == LM_CH_MAX_I ? mi : ch == LM_CH_MEAN_I ? mean_i : ch == LM_CH_MIN_Z ? nz
-                     : ch == LM_CH_MAX_Z ? xz : ch == LM_CH_MEAN_Z ? mean_z : dens;
-            };
-            uint32_t pk = pick(ch0);
-            if (nch > 1) pk |= pick(ch1) << 8;
-            if (nch > 2) pk |= pick(ch2) << 16;
-            if (nch > 3) pk |= pick(ch3) << 24;
-            if (out.proj && inside) {
-                for (int c = 0; c < nch; ++c)
-                    out.proj[((size_t)c * kp.oH + orow0 + lr) * kp.W + gcol0 + lc] =
-                        __fdiv_rn((float)((pk >> (8 * c)) & 0xFFu), 255.0f);
+            if (out.count16) {
+                uint16_t *dst = out.count16 + grow;
+                if (c16_fast) {
+                    reinterpret_cast<uint32_t *>(dst)[0] = k16[0] | (k16[1] << 16);
+                    reinterpret_cast<uint32_t *>(dst)[1] = k16[2] | (k16[3] << 16);
+                } else {
+                    for (int e = 0; e < 4; ++e)
+                        if (lc0 + e < ncols) dst[e] = (uint16_t)k16[e];
+                }
             }
-            packed[cell] = pk;
-            if (NW >= 2) cnt16[cell] = cnt < 65535u ? cnt : 65535u;
+            if (out.proj) {
+                for (int c = 0; c < nch; ++c) {
+                    float *dst = out.proj + (size_t)c * gcells + grow;
+                    for (int e = 0; e < 4; ++e)
+                        if (lc0 + e < ncols) dst[e] = __fdiv_rn((float)((pk[e] >> (8 * c)) & 0xFFu), 255.0f);
+                }
+            }
         }
         if (overflow) atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_CELL_OVERFLOW);
-        __syncthreads();
+    }
+}
 
-        // ---- coalesced tile write-out
-        if (out.image) {
-            switch (kp.nch) {
-                case 1: write_image_rows<1>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
-                case 2: write_image_rows<2>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
-                case 3: write_image_rows<3>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
-                default: write_image_rows<4>(packed, out.image, kp.W, orow0, gcol0, nrows, ncols, tid); break;
-            }
+// ------------------------------------------------------------------------------------------
+// self-test: mean_small == integer (sum + count/2) / count for EVERY count in [1,4095], sum <= 255*count
+// ------------------------------------------------------------------------------------------
+__global__ void selftest_mean_kernel(unsigned long long *out) {
+    unsigned long long bad = 0, n = 0;
+    for (uint32_t cnt = 1 + blockIdx.x; cnt <= PK_CNT_MAX; cnt += gridDim.x) {
+        for (uint32_t sum = threadIdx.x; sum <= 255u * cnt; sum += blockDim.x) {
+            ++n;
+            if (mean_small(sum, cnt) != (sum + (cnt >> 1)) / cnt) ++bad;
         }
-        if (NW >= 2 && out.count16) {
-            for (int it = tid; it < nrows * ncols; it += RED_THREADS) {
-                const int lr = it / ncols, lc = it - lr * ncols;
-                out.count16[(size_t)(orow0 + lr) * kp.W + gcol0 + lc] = (uint16_t)cnt16[(lr << TILE_W_LOG2) + lc];
-            }
-        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&out[0], bad);
+        atomicAdd(&out[1], n);
     }
 }
 
@@ -1290,6 +1332,16 @@ int lm_bev_selftest_div(float divisor, unsigned long long *out2_dev, void *strea
     selftest_div_kernel<<<sm_count() * 16, 256, 0, st>>>(divisor, 1.0f / divisor, out2_dev);
     e = cudaGetLastError();
     return e == cudaSuccess ? LM_OK : cuda_fail(e, "selftest_div launch");
+}
+
+int lm_bev_selftest_mean(unsigned long long *out2_dev, void *stream) {
+    if (!out2_dev) return fail(LM_ERR_INVALID, "selftest_mean: NULL output");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(out2_dev, 0, 16, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    selftest_mean_kernel<<<sm_count() * 8, 256, 0, st>>>(out2_dev);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "selftest_mean launch");
 }
 
 }  // extern "C"

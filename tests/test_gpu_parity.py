@@ -217,3 +217,14 @@ def test_banded_raw_accumulators(bev, band):
     assert np.array_equal(out["image"].cpu().numpy(), O.finalize(acc, spec)["image"])
     for plane in (O.ACC_COUNT, O.ACC_SUM_Z, O.ACC_MAX_I):      # the planes max_i / mean_z / density need
         assert np.array_equal(got[plane, :band], acc[plane, :band]) and np.array_equal(got[plane, -band:], acc[plane, -band:])
+
+
+def test_exact_mean_exhaustive(bev, native_lib):
+    """reduce_tiles derives mean channels with a float reciprocal when count <= 4095; it must equal
+    the integer (sum + count/2) // count for every possible (count, sum)."""
+    from lanemapping_b200 import _cabi
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _cabi.check(native_lib.lm_bev_selftest_mean(out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    bad, n = (int(v) for v in out.cpu())
+    assert n == sum(255 * c + 1 for c in range(1, 4096)) and bad == 0
