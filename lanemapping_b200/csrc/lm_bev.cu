@@ -58,7 +58,7 @@ constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
 constexpr int MAX_BIN_CTAS = 148 * (LM_BIN_MIN_CTAS + 1);   // most bin CTAs ever launched (B200: 148 SMs)
 constexpr int RED_THREADS = 512;
 constexpr int RED_MIN_CTAS = 2;          // shared-memory tiles are sized so that two CTAs fit per SM
-constexpr int MAX_TILES = 9000;           // bin_points keeps 20 B of append state per tile in shared memory
+constexpr int MAX_TILES = 15000;          // bin_points keeps 4 * (1 + NSLOT) B of append state per tile in shared memory
 constexpr uint32_t INVALID_U32 = 0xFFFFFFFFu;
 
 // accumulator planes held in shared memory by reduce_tiles (bit mask)
@@ -957,15 +957,15 @@ int pick_mask(int need, bool count16) {
         if ((m & need) == need && !(count16 && popc6(m) < 2)) return m;
     return M_ALL;
 }
-// tile height so that NW planes of 128 x TH u32 stay <= 96 KB: two reduce CTAs per SM overlap
-// one tile's zero/finish/write phases with the other's streaming phase
+// tile height: 128 rows for a single plane, else 64 rows (two reduce CTAs per SM up to 3 planes,
+// so that one tile's finish/write pass overlaps the other's streaming; one CTA per SM beyond)
 int tile_h_log2_for(int mask) {
     const int nw = popc6(mask);
     if (const char *e = getenv("LM_BEV_TILE_H_LOG2")) {      // tuning knob (5..7); must keep NW planes <= 227 KB
         const int v = atoi(e);
-        if (v >= 5 && v <= 7 && nw * (128 << v) * 4 <= 220 * 1024) return v;
+        if (v >= 5 && v <= 7 && nw * (128 << v) * 4 <= 200 * 1024) return v;
     }
-    return nw <= 1 ? 7 : (nw <= 3 ? 6 : 5);
+    return nw <= 1 ? 7 : 6;      // 128 x 64 tiles: 2 CTAs/SM up to 3 planes, 1 CTA/SM (<= 192 KB) up to 6
 }
 
 int validate(const lm_bev_params *p) {
