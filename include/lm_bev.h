@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LM_BEV_ABI_VERSION 1
+#define LM_BEV_ABI_VERSION 2
 
 /* u8 image channels.  Index 1 of a 3-channel cropped_tiff must be an elevation channel:
  * reference baseline/utils/coor_img2pc.py:150 reads img[row, col, 1] as height. */
@@ -142,6 +142,32 @@ enum { LM_STAGE_BIN = 1, LM_STAGE_INDEX = 2, LM_STAGE_REDUCE = 4, LM_STAGE_ALL =
 int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
                             void *workspace_dev, size_t workspace_bytes,
                             const lm_bev_outputs *out, void *stream, int stages);
+
+/* Batched call (BASELINE.json configs[4]: on-the-fly rasterisation of a DataLoader batch into
+ * sample['proj'], reference baseline/models/pcencoder/postprojector.py:79-82).  n_samples clouds
+ * are rasterised onto n_samples rasters of the SAME shape p (height, width, resolutions, channels,
+ * intensity range); sample s takes its origin and window shift from geoms[s] instead of p.  Up to
+ * 32 samples share one set of launches (they are stacked along the rows internally), so a batch
+ * of 1152^2 crops runs at the speed of one large raster instead of n_samples small ones.
+ *   points_dev[s], n_points[s]   HOST arrays of device pointers / counts (one cloud per sample)
+ *   out->image_dev  [n_samples][height][width][n_channels] u8
+ *   out->count16_dev [n_samples][height][width] u16
+ *   out->proj_dev   [n_samples][n_channels][height][width] f32   (= torch.stack of the loader's tensors)
+ *   out->acc_dev    must be NULL
+ * Results are bit-identical to n_samples separate lm_bev_rasterize calls.                        */
+typedef struct lm_bev_sample_geom {
+    float   bev_img_offset[2];
+    float   local_min_ele;
+    int32_t row0, col0;
+    int32_t reserved;
+} lm_bev_sample_geom;
+
+int lm_bev_workspace_bytes_batch(const lm_bev_params *p, int32_t n_samples, int64_t n_points_total,
+                                 const lm_bev_outputs *out, size_t *bytes);
+int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_bev_sample_geom *geoms,
+                           const float *const *points_dev, const int64_t *n_points,
+                           void *workspace_dev, size_t workspace_bytes,
+                           const lm_bev_outputs *out, void *stream);
 
 /* dst = merge(dst, src) over rows [0,rows) of two accumulator sets whose planes are
  * dst_plane_stride / src_plane_stride ELEMENTS apart (count, sums: add; max: max; min: min).

@@ -8,7 +8,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ALGO_BINNED, ALGO_DIRECT = 0, 1
 STAGE_BIN, STAGE_INDEX, STAGE_REDUCE, STAGE_ALL = 1, 2, 4, 7
 DEV_ERR_POOL, DEV_ERR_CELL_OVERFLOW = 1, 2
@@ -39,6 +39,24 @@ class LmBevOutputs(C.Structure):
     ]
 
 
+class LmBevSampleGeom(C.Structure):
+    _fields_ = [
+        ("bev_img_offset", C.c_float * 2),
+        ("local_min_ele", C.c_float),
+        ("row0", C.c_int32), ("col0", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class LmLasXform(C.Structure):
+    _fields_ = [
+        ("record_length", C.c_int32), ("reserved", C.c_int32),
+        ("scale", C.c_double * 3), ("offset", C.c_double * 3),
+        ("las_read_offset", C.c_double * 3), ("translation", C.c_double * 3),
+        ("rot", C.c_double * 9),
+    ]
+
+
 class LmBevStats(C.Structure):
     _fields_ = [
         ("error", C.c_uint32), ("n_chunks", C.c_uint32),
@@ -56,6 +74,14 @@ SYMBOLS = {
                                    C.POINTER(LmBevOutputs), C.c_void_p]),
     "lm_bev_rasterize_stages": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
                                           C.POINTER(LmBevOutputs), C.c_void_p, C.c_int]),
+    "lm_bev_workspace_bytes_batch": (C.c_int, [C.POINTER(LmBevParams), C.c_int32, C.c_int64, C.POINTER(LmBevOutputs),
+                                               C.POINTER(C.c_size_t)]),
+    "lm_bev_rasterize_batch": (C.c_int, [C.POINTER(LmBevParams), C.c_int32, C.POINTER(LmBevSampleGeom),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p, C.c_size_t,
+                                         C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_las_decode": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(LmLasXform), C.c_void_p, C.c_void_p]),
+    "lm_bev_rasterize_las": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.POINTER(LmLasXform), C.c_void_p,
+                                       C.c_size_t, C.POINTER(LmBevOutputs), C.c_void_p]),
     "lm_bev_acc_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "lm_bev_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32,
                                   C.POINTER(LmBevOutputs), C.c_void_p]),
@@ -96,6 +122,18 @@ def lib() -> C.CDLL:
 def check(code: int) -> None:
     if code != 0:
         raise LmBevError(code, lib().lm_bev_last_error().decode("utf-8", "replace"))
+
+
+def make_las_xform(record_length, scale, offset, las_read_offset=(0.0, 0.0, 0.0), translation=(0.0, 0.0, 0.0),
+                   rot=(1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)) -> LmLasXform:
+    x = LmLasXform()
+    x.record_length = int(record_length)
+    for k in range(3):
+        x.scale[k], x.offset[k] = float(scale[k]), float(offset[k])
+        x.las_read_offset[k], x.translation[k] = float(las_read_offset[k]), float(translation[k])
+    for k in range(9):
+        x.rot[k] = float(rot[k])
+    return x
 
 
 def make_params(spec) -> LmBevParams:

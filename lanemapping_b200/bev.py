@@ -110,6 +110,33 @@ class BevRasterizer:
                 self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream, int(stages)))
         return out
 
+    def rasterize_las(self, records: torch.Tensor, n_points: int, xform, out: Optional[Dict[str, torch.Tensor]] = None,
+                      stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+        """Rasterise straight from the point-data block of a LAS file (``lm_bev_rasterize_las``):
+        ``records`` is a uint8 device tensor of ``n_points * record_length`` bytes as on disk,
+        ``xform`` comes from :func:`las_xform`.  The decode runs inside the first kernel."""
+        if self.algo != "binned":
+            raise ValueError("rasterize_las runs the binned path only")
+        n = int(n_points)
+        if records.dtype != torch.uint8 or not records.is_contiguous() or records.numel() < n * xform.record_length:
+            raise ValueError("records must be a contiguous uint8 tensor of n_points * record_length bytes")
+        if n > self.max_points:
+            raise ValueError(f"{n} points > max_points={self.max_points} this workspace was sized for")
+        if out is None:
+            out = self.alloc_outputs()
+        o = _cabi.LmBevOutputs()
+        o.image_dev = _ptr(out.get("image"))
+        o.count16_dev = _ptr(out.get("count16"))
+        o.proj_dev = _ptr(out.get("proj"))
+        o.acc_dev = _ptr(out.get("acc"))
+        o.acc_band = self.acc_band
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.lm_bev_rasterize_las(
+                C.byref(self._params), records.data_ptr() if n else None, n, C.byref(xform),
+                self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream))
+        return out
+
     def stats(self) -> dict:
         """Device-side counters of the last call (synchronises)."""
         raw = self.workspace[:C.sizeof(_cabi.LmBevStats)].cpu().numpy().tobytes()
@@ -123,6 +150,132 @@ class BevRasterizer:
             raise RuntimeError("liblm_bev: record chunk pool exhausted (workspace too small)")
         if s["error"] & _cabi.DEV_ERR_CELL_OVERFLOW:
             raise RuntimeError("liblm_bev: a cell received >= 2^24 points; u32 sums may have wrapped")
+
+
+class BatchRasterizer:
+    """B equally-shaped rasters per call (``lm_bev_rasterize_batch``): the samples of a DataLoader
+    batch are stacked along the rows inside the library and share one set of launches.
+
+    ``spec`` gives the common shape / resolutions / channels; sample ``b`` takes its origin from
+    ``specs[b]`` (``bev_img_offset``, ``local_min_ele``, ``row0``, ``col0``) when given.
+    Outputs: ``image`` u8 [B,H,W,C], ``count16`` u16 [B,H,W], ``proj`` f32 [B,C,H,W].
+    """
+
+    def __init__(self, spec: BevSpec, batch: int, max_points_total: int, device: torch.device | str = "cuda",
+                 outputs: Iterable[str] = ("proj",)):
+        outputs = tuple(outputs)
+        if not outputs or any(o not in ("image", "count16", "proj") for o in outputs):
+            raise ValueError("outputs must be a non-empty subset of ('image', 'count16', 'proj')")
+        self.spec, self.batch, self.outputs = spec, int(batch), outputs
+        self.max_points_total = int(max_points_total)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("lanemapping_b200 runs on CUDA devices only (no CPU fallback)")
+        self._lib = _cabi.lib()
+        self._params = _cabi.make_params(spec)
+        o = _cabi.LmBevOutputs()
+        for k in outputs:
+            setattr(o, k + "_dev", 1)
+        nbytes = C.c_size_t(0)
+        _cabi.check(self._lib.lm_bev_workspace_bytes_batch(C.byref(self._params), self.batch, self.max_points_total,
+                                                           C.byref(o), C.byref(nbytes)))
+        self.workspace = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
+
+    def alloc_outputs(self) -> Dict[str, torch.Tensor]:
+        B, H, W, Cn = self.batch, self.spec.height, self.spec.width, self.spec.n_channels
+        out: Dict[str, torch.Tensor] = {}
+        if "image" in self.outputs:
+            out["image"] = torch.empty((B, H, W, Cn), dtype=torch.uint8, device=self.device)
+        if "count16" in self.outputs:
+            out["count16"] = torch.empty((B, H, W), dtype=torch.uint16, device=self.device)
+        if "proj" in self.outputs:
+            out["proj"] = torch.empty((B, Cn, H, W), dtype=torch.float32, device=self.device)
+        return out
+
+    def __call__(self, points, specs=None, out: Optional[Dict[str, torch.Tensor]] = None,
+                 stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+        B = len(points)
+        if B < 1 or B > self.batch:
+            raise ValueError(f"expected 1..{self.batch} clouds, got {B}")
+        if specs is not None and len(specs) != B:
+            raise ValueError("specs must have one entry per cloud")
+        geoms = (_cabi.LmBevSampleGeom * B)()
+        ptrs = (C.c_void_p * B)()
+        counts = (C.c_int64 * B)()
+        total = 0
+        for b, pts in enumerate(points):
+            if pts.device.type != "cuda" or pts.device.index != self.workspace.device.index:
+                raise ValueError("points must live on the rasteriser's device")
+            if pts.dtype != torch.float32 or pts.dim() != 2 or pts.shape[1] != 4 or not pts.is_contiguous():
+                raise ValueError("points must be contiguous float32 [N,4] tensors (x, y, z, intensity)")
+            sp = self.spec if specs is None else specs[b]
+            if specs is not None and (sp.height, sp.width, sp.img_reso, sp.ele_reso, sp.channels, sp.inten_min,
+                                      sp.inten_max) != (self.spec.height, self.spec.width, self.spec.img_reso,
+                                                        self.spec.ele_reso, self.spec.channels, self.spec.inten_min,
+                                                        self.spec.inten_max):
+                raise ValueError("batched samples must share shape, resolutions, channels and intensity range")
+            geoms[b].bev_img_offset[0], geoms[b].bev_img_offset[1] = sp.bev_img_offset
+            geoms[b].local_min_ele = sp.local_min_ele
+            geoms[b].row0, geoms[b].col0 = sp.row0, sp.col0
+            n = int(pts.shape[0])
+            ptrs[b] = pts.data_ptr() if n else None
+            counts[b] = n
+            total += n
+        if total > self.max_points_total:
+            raise ValueError(f"{total} points > max_points_total={self.max_points_total} this workspace was sized for")
+        if out is None:
+            out = self.alloc_outputs()
+            out = {k: v[:B] for k, v in out.items()}
+        o = _cabi.LmBevOutputs()
+        o.image_dev = _ptr(out.get("image"))
+        o.count16_dev = _ptr(out.get("count16"))
+        o.proj_dev = _ptr(out.get("proj"))
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.lm_bev_rasterize_batch(C.byref(self._params), B, geoms, ptrs, counts,
+                                                         self.workspace.data_ptr(), self.workspace.numel(),
+                                                         C.byref(o), st.cuda_stream))
+        return out
+
+    def stats(self) -> dict:
+        raw = self.workspace[:C.sizeof(_cabi.LmBevStats)].cpu().numpy().tobytes()
+        s = _cabi.LmBevStats.from_buffer_copy(raw)
+        return {"error": int(s.error), "n_chunks": int(s.n_chunks), "n_valid": int(s.n_valid),
+                "n_tiles": int(s.n_tiles)}
+
+
+def las_xform(header, params=None):
+    """The decode parameters of one LAS file: ``header`` is a :class:`lanemapping_b200.las.LasHeader`,
+    ``params`` the crop's :class:`lanemapping_b200.sidecar.PcImgParams` (None = world frame: no read
+    offset, identity rotation).  rot = R(q)^T, the inverse of reference
+    baseline/utils/coor_img2pc.py:163-171."""
+    if params is None:
+        return _cabi.make_las_xform(header.record_length, header.scale, header.offset)
+    from .sidecar import quat_to_matrix
+    rot = quat_to_matrix(params.las_rotation_trans_quan[3:]).T.reshape(9)
+    return _cabi.make_las_xform(header.record_length, header.scale, header.offset, params.las_read_offset,
+                                params.las_rotation_trans_quan[:3], rot)
+
+
+def decode_las(records: torch.Tensor, n_points: int, xform, out: Optional[torch.Tensor] = None,
+               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """LAS point records (uint8 device tensor, as on disk) -> float32 [n,4] (x, y, z, intensity) in the
+    raster-local frame (``lm_las_decode``): the GPU replacement of the reference's ``read_las``
+    (baseline/datasets/laserlane_proposals.py:618-636) up to its intensity normalisation."""
+    n = int(n_points)
+    if records.device.type != "cuda":
+        raise RuntimeError("lanemapping_b200 runs on CUDA devices only (no CPU fallback)")
+    if records.dtype != torch.uint8 or not records.is_contiguous() or records.numel() < n * xform.record_length:
+        raise ValueError("records must be a contiguous uint8 tensor of n_points * record_length bytes")
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.float32, device=records.device)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (n, 4) or not out.is_contiguous() or out.device != records.device:
+        raise ValueError("out must be a contiguous float32 [n,4] tensor on the records' device")
+    st = stream if stream is not None else torch.cuda.current_stream(records.device)
+    with torch.cuda.device(records.device):
+        _cabi.check(_cabi.lib().lm_las_decode(records.data_ptr() if n else None, n, C.byref(xform),
+                                              out.data_ptr() if n else None, st.cuda_stream))
+    return out
 
 
 def rasterize(points: torch.Tensor, spec: BevSpec, algo: str = "binned",

@@ -20,6 +20,8 @@
 // Bit-exactness: all float steps are single IEEE-754 binary32 operations (__fsub_rn/__fdiv_rn,
 // floorf, rintf); compile with -fmad=false and never with -use_fast_math.
 #include "lm_bev.h"
+#include "lm_las.h"
+#include "lm_dev.cuh"
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -84,6 +86,7 @@ struct KParams {
     int band;       // > 0: raw accumulators are wanted for output rows [0,band) and [oH-band,oH) only
     int oH, orow;   // height of the output buffers and this window's first row inside them
                     // (a raster with more tiles than one launch handles is done as row windows)
+    int bH;         // > 0: batched call, the raster is a stack of samples of bH rows each (proj is [B][C][bH][W])
 };
 
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
@@ -156,12 +159,19 @@ __device__ __forceinline__ bool div_fast_ok(float a) { return fabsf(a) >= 0x1p-4
 // The conversions use the saturating F2I modes, which give the same integers as the spec's
 // floorf / rintf / clamp-then-truncate on every input (huge values saturate and fall outside the
 // window or into the clamp; NaN converts to 0 and is rejected / clamped exactly as fmaxf would).
+// the part of the geometry that differs between the samples of a batched call (lm_bev_rasterize_batch)
+struct Geo {
+    float off0, off1, zmin;
+    int row0, col0, H;
+};
+__device__ __forceinline__ Geo geo_of(const KParams &k) { return Geo{k.off0, k.off1, k.zmin, k.row0, k.col0, k.H}; }
+
 __device__ __forceinline__ bool keys_from_quotients(float qx, float qy, float qz, float inten, const KParams &k,
-                                                    int &lrow, int &lcol, uint32_t &iq, uint32_t &zq) {
-    const uint32_t ur = (uint32_t)__float2int_rd(qx) - (uint32_t)k.row0;      // floor, then window shift
-    const uint32_t uc = (uint32_t)__float2int_rd(qy) - (uint32_t)k.col0;
+                                                    const Geo &g, int &lrow, int &lcol, uint32_t &iq, uint32_t &zq) {
+    const uint32_t ur = (uint32_t)__float2int_rd(qx) - (uint32_t)g.row0;      // floor, then window shift
+    const uint32_t uc = (uint32_t)__float2int_rd(qy) - (uint32_t)g.col0;
     const float s = __fadd_rn(qx, qy);                                        // NaN iff a quotient is NaN
-    const bool valid = ur < (uint32_t)k.H && uc < (uint32_t)k.W && s == s;    // never clamped, NaN dropped
+    const bool valid = ur < (uint32_t)g.H && uc < (uint32_t)k.W && s == s;    // never clamped, NaN dropped
     lrow = (int)ur;
     lcol = (int)uc;
     // inverse of coor_img2pc.py:150: round-half-even, clamp to the u8 range, NaN -> 0
@@ -175,10 +185,14 @@ __device__ __forceinline__ bool keys_from_quotients(float qx, float qy, float qz
 }
 
 // the spec, literally: IEEE division (inverse of reference baseline/utils/coor_img2pc.py:136-139,150)
+__device__ __forceinline__ bool quantise_ieee(const float4 p, const KParams &k, const Geo &g, int &lrow, int &lcol,
+                                              uint32_t &iq, uint32_t &zq) {
+    return keys_from_quotients(__fdiv_rn(__fsub_rn(p.x, g.off0), k.reso0), __fdiv_rn(__fsub_rn(p.y, g.off1), k.reso1),
+                               __fdiv_rn(__fsub_rn(p.z, g.zmin), k.zreso), p.w, k, g, lrow, lcol, iq, zq);
+}
 __device__ __forceinline__ bool quantise_ieee(const float4 p, const KParams &k, int &lrow, int &lcol,
                                               uint32_t &iq, uint32_t &zq) {
-    return keys_from_quotients(__fdiv_rn(__fsub_rn(p.x, k.off0), k.reso0), __fdiv_rn(__fsub_rn(p.y, k.off1), k.reso1),
-                               __fdiv_rn(__fsub_rn(p.z, k.zmin), k.zreso), p.w, k, lrow, lcol, iq, zq);
+    return quantise_ieee(p, k, geo_of(k), lrow, lcol, iq, zq);
 }
 
 // same result through div_const; the caller must check that lo/hi (running min/max of the
@@ -189,7 +203,7 @@ __device__ __forceinline__ bool quantise_fast(const float4 p, const KParams &k, 
     lo = fminf(lo, fminf(fabsf(dx), fminf(fabsf(dy), fabsf(dz))));
     hi = fmaxf(hi, fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz))));
     return keys_from_quotients(div_const(dx, k.reso0, k.rreso0), div_const(dy, k.reso1, k.rreso1),
-                               div_const(dz, k.zreso, k.rzreso), p.w, k, lrow, lcol, iq, zq);
+                               div_const(dz, k.zreso, k.rzreso), p.w, k, geo_of(k), lrow, lcol, iq, zq);
 }
 // NaN dividends propagate identically through both paths (fminf/fmaxf skip them), so only the
 // magnitudes of the finite ones have to be in range; an all-NaN thread fails the test and takes
@@ -301,52 +315,6 @@ __global__ void crop_tiles_kernel(const uint8_t *__restrict__ img, int H, int W,
 }
 
 // ------------------------------------------------------------------------------------------
-// TMA 1-D bulk copy (global -> shared) completing on an mbarrier: one thread moves a whole batch
-// of packed point records; no per-thread address math, no registers held while in flight
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile("{\n"
-                 ".reg .pred p;\n"
-                 "LM_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra LM_DONE;\n"
-                 "bra LM_WAIT;\n"
-                 "LM_DONE:\n"
-                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-// Shared-memory accesses of the hot loop go through explicit 32-bit shared addresses: the base is
-// computed once and stays in a register (the generic form re-derives the shared window per access).
-__device__ __forceinline__ float4 lds_f4(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
-    return old;
-}
-
-// ------------------------------------------------------------------------------------------
 // LM_ALGO_BINNED stage 1: bin_points
 // ------------------------------------------------------------------------------------------
 // tile_nchunks counts 512-record PIECES (the reduce kernel's work unit), a chunk holds HALVES of them
@@ -372,13 +340,35 @@ constexpr int NSLOT = BIN_BATCH <= CHUNK_RECS ? 2 : 4;
 constexpr int STASH = 128;            // chunk ids fetched per refill
 constexpr int STASH_LOW = 32;         // refill when fewer than this remain (the remainder is abandoned)
 
-__global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
-                                                                               long long n, Ws ws) {
+// A batched call (lm_bev_rasterize_batch) rasterises up to MAX_BATCH equally-shaped samples as ONE
+// stacked raster of n_samples * bH rows: sample s owns the 1024-point batches [first[s], first[s+1])
+// and brings its own origin / window shift; everything after the keys is shared.
+constexpr int MAX_BATCH = 32;
+struct BatchTab {
+    const float4 *pts[MAX_BATCH];
+    uint32_t first[MAX_BATCH + 1];
+    uint32_t count[MAX_BATCH];
+    float off0[MAX_BATCH], off1[MAX_BATCH], zmin[MAX_BATCH];
+    int row0[MAX_BATCH], col0[MAX_BATCH];
+    int nb, bH;
+};
+
+// LAS: the input is the point-data block of an uncompressed LAS file (record_length bytes per point)
+// and the decode of lm_dev.cuh::las_decode_record runs on the staged bytes; no float4 copy of the
+// cloud ever exists in HBM.
+template <bool BATCHED, bool LAS>
+__device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 *__restrict__ pts, long long n, const Ws &ws,
+                                                const BatchTab *btp, const LasXform *xfp) {
+    const BatchTab &bt = *btp;       // only dereferenced when BATCHED
+    const LasXform &xf = *xfp;       // only dereferenced when LAS
+    const uint32_t rec_bytes = LAS ? (uint32_t)xf.record_length : 16u;
+    // one stage buffer: a full batch of records, 16-byte granular, + one spare 16 B (whole words are read)
+    const uint32_t stage_bytes = LAS ? ((BIN_BATCH * rec_bytes + 15u) & ~15u) + 16u : BIN_BATCH * 16u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = kp.T;
     // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u32
     uint32_t sm_stage = smem_u32(smem_raw);
-    uint32_t sm_pos = sm_stage + 2u * BIN_BATCH * 16u;
+    uint32_t sm_pos = sm_stage + 2u * stage_bytes;
     uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
     // keep the three bases in registers: without this the compiler re-derives them (window base +
     // offsets, ~5 instructions) at every use because they are cheap to rematerialise
@@ -393,33 +383,64 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
     for (int t = tid; t < T; t += BIN_THREADS) sts_u32(sm_pos + 4u * t, 0u);
     __syncthreads();
 
-    const long long nb = (n + BIN_BATCH - 1) / BIN_BATCH;
+    const long long nb = BATCHED ? (long long)bt.first[bt.nb] : (n + BIN_BATCH - 1) / BIN_BATCH;
     const long long b0 = nb * blockIdx.x / gridDim.x, b1 = nb * (blockIdx.x + 1) / gridDim.x;
     const int my_batches = (int)(b1 - b0);
-    const float4 *src = pts + b0 * BIN_BATCH;                                // this CTA's contiguous range
-    const uint32_t tail = (uint32_t)(n - (nb - 1) * BIN_BATCH);             // points in the very last batch
-    auto batch_points = [&](int k) -> uint32_t { return b0 + k == nb - 1 ? tail : (uint32_t)BIN_BATCH; };
-    if (tid == 0 && my_batches > 0) bulk_load(smem_raw, src, batch_points(0) * 16u, &s_bar[0]);
+    const uint32_t tail = BATCHED ? 0u : (uint32_t)(n - (nb - 1) * BIN_BATCH);   // points in the very last batch
+    // batch k of this CTA: where its records start and how many there are (samp = its sample, batched
+    // calls only; batches are visited in order, so the sample cursor only ever moves forward)
+    auto batch_src = [&](int k, int &samp, uint32_t &np) -> const void * {
+        const long long g = b0 + k;
+        if (BATCHED) {
+            while (g >= (long long)bt.first[samp + 1]) ++samp;
+            const uint32_t lb = (uint32_t)(g - bt.first[samp]);
+            const uint32_t rem = bt.count[samp] - lb * (uint32_t)BIN_BATCH;
+            np = rem < (uint32_t)BIN_BATCH ? rem : (uint32_t)BIN_BATCH;
+            return bt.pts[samp] + (size_t)lb * BIN_BATCH;
+        }
+        np = g == nb - 1 ? tail : (uint32_t)BIN_BATCH;
+        if (LAS) return reinterpret_cast<const unsigned char *>(pts) + (size_t)g * BIN_BATCH * rec_bytes;
+        return pts + g * BIN_BATCH;
+    };
+    // bytes of a batch as the bulk copy wants them (multiples of 16; a LAS tail may read up to 15
+    // bytes past its last record -- the caller's buffer is padded, lm_las.h)
+    auto batch_bytes = [&](uint32_t np) -> uint32_t { return LAS ? (np * rec_bytes + 15u) & ~15u : np * 16u; };
+    int samp = 0, samp_pf = 0;                                               // sample cursors: compute / prefetch (thread 0)
+    if (tid == 0 && my_batches > 0) {
+        uint32_t np;
+        const void *src = batch_src(0, samp_pf, np);
+        bulk_load(smem_raw, src, batch_bytes(np), &s_bar[0]);
+    }
+    Geo geo = geo_of(kp);
+    int row_shift = 0;                                                       // first row of the sample in the stacked raster
 
     for (int k = 0; k < my_batches; ++k) {
         const uint32_t buf = (uint32_t)k & 1u;
         // the NEXT batch starts flying now, into the buffer that was consumed one batch ago
-        if (tid == 0 && k + 1 < my_batches)
-            bulk_load(smem_raw + (buf ^ 1u) * (BIN_BATCH * 16u), src + (size_t)(k + 1) * BIN_BATCH,
-                      batch_points(k + 1) * 16u, &s_bar[buf ^ 1u]);
+        if (tid == 0 && k + 1 < my_batches) {
+            uint32_t np;
+            const void *src = batch_src(k + 1, samp_pf, np);
+            bulk_load(smem_raw + (buf ^ 1u) * stage_bytes, src, batch_bytes(np), &s_bar[buf ^ 1u]);
+        }
+        uint32_t npts;
+        batch_src(k, samp, npts);
+        if (BATCHED) {
+            geo = Geo{bt.off0[samp], bt.off1[samp], bt.zmin[samp], bt.row0[samp], bt.col0[samp], bt.bH};
+            row_shift = samp * bt.bH;
+        }
         // stash refill (thread 0): the global atomic is in flight while everybody computes keys
         const uint32_t act = s_active;
         uint32_t refill = 0;
         const bool do_refill = tid == 0 && (int)(s_stash[act][1] - s_stash[act][0]) < STASH_LOW;
         if (do_refill) refill = atomicAdd(&ws.ctl->pool_cursor, (uint32_t)STASH) + 1u;
 
-        const uint32_t npts = batch_points(k);
         mbar_wait(&s_bar[buf], ((uint32_t)k >> 1) & 1u);     // this batch's records have landed
         float4 p[BIN_PPT];
-        const uint32_t my_stage = sm_stage + buf * (BIN_BATCH * 16u) + (uint32_t)tid * 16u;
+        const uint32_t my_stage = sm_stage + buf * stage_bytes + (uint32_t)tid * rec_bytes;
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
-            p[j] = lds_f4(my_stage + (uint32_t)j * (BIN_THREADS * 16u));
+            if (LAS) p[j] = las_decode_record(my_stage + (uint32_t)j * (BIN_THREADS * rec_bytes), xf);
+            else p[j] = lds_f4(my_stage + (uint32_t)j * (BIN_THREADS * 16u));
         }
         if (npts < (uint32_t)BIN_BATCH) {                        // only the very last batch of the cloud
 #pragma unroll
@@ -436,9 +457,9 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
             float2 qxy[BIN_PPT];
             float qz[BIN_PPT];
             float lo = 0x1p100f, hi = 0.0f;
-            const float2 noff = make_float2(-kp.off0, -kp.off1), reso2 = make_float2(kp.reso0, kp.reso1),
+            const float2 noff = make_float2(-geo.off0, -geo.off1), reso2 = make_float2(kp.reso0, kp.reso1),
                          rr2 = make_float2(kp.rreso0, kp.rreso1);
-            const float2 nzmin2 = make_float2(-kp.zmin, -kp.zmin), zreso2 = make_float2(kp.zreso, kp.zreso),
+            const float2 nzmin2 = make_float2(-geo.zmin, -geo.zmin), zreso2 = make_float2(kp.zreso, kp.zreso),
                          rz2 = make_float2(kp.rzreso, kp.rzreso);
 #pragma unroll
             for (int j = 0; j < BIN_PPT; ++j) {
@@ -459,10 +480,14 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
             if (kp.fast_div && fast_range_ok(lo, hi)) {
 #pragma unroll
                 for (int j = 0; j < BIN_PPT; ++j)
-                    ok[j] = keys_from_quotients(qxy[j].x, qxy[j].y, qz[j], p[j].w, kp, r[j], c[j], iq[j], zq[j]);
+                    ok[j] = keys_from_quotients(qxy[j].x, qxy[j].y, qz[j], p[j].w, kp, geo, r[j], c[j], iq[j], zq[j]);
             } else {                                            // rare: 0, denormal-scale, huge, inf or all-NaN dividends
 #pragma unroll
-                for (int j = 0; j < BIN_PPT; ++j) ok[j] = quantise_ieee(p[j], kp, r[j], c[j], iq[j], zq[j]);
+                for (int j = 0; j < BIN_PPT; ++j) ok[j] = quantise_ieee(p[j], kp, geo, r[j], c[j], iq[j], zq[j]);
+            }
+            if (BATCHED) {
+#pragma unroll
+                for (int j = 0; j < BIN_PPT; ++j) r[j] += row_shift;
             }
 #pragma unroll
             for (int j = 0; j < BIN_PPT; ++j) {
@@ -533,6 +558,67 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
     }
     for (int o = 16; o; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
     if ((tid & 31) == 0 && my_valid) atomicAdd((unsigned long long *)&ws.stats->n_valid, (unsigned long long)my_valid);
+}
+
+
+__global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
+                                                                               long long n, Ws ws) {
+    bin_points_body<false, false>(kp, pts, n, ws, nullptr, nullptr);
+}
+__global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_batch_kernel(KParams kp, const __grid_constant__ BatchTab bt,
+                                                                                     Ws ws) {
+    bin_points_body<true, false>(kp, nullptr, 0, ws, &bt, nullptr);
+}
+__global__ void __launch_bounds__(BIN_THREADS, 3) bin_points_las_kernel(KParams kp, const __grid_constant__ LasXform xf,
+                                                                       const unsigned char *__restrict__ recs, long long n, Ws ws) {
+    bin_points_body<false, true>(kp, reinterpret_cast<const float4 *>(recs), n, ws, nullptr, &xf);
+}
+
+// ------------------------------------------------------------------------------------------
+// LAS point records -> packed float4 (lm_las_decode): the same TMA-staged loop without the binning
+// ------------------------------------------------------------------------------------------
+constexpr int LAS_THREADS = 256;
+constexpr int LAS_TILE = 1024;           // records per stage buffer
+__host__ __device__ inline uint32_t las_stage_bytes(uint32_t rec_bytes, uint32_t records) {
+    return ((records * rec_bytes + 15u) & ~15u) + 16u;
+}
+
+__global__ void __launch_bounds__(LAS_THREADS) las_decode_kernel(const __grid_constant__ LasXform xf,
+                                                                 const unsigned char *__restrict__ recs, long long n,
+                                                                 float4 *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int tid = threadIdx.x;
+    const uint32_t rec_bytes = (uint32_t)xf.record_length;
+    const uint32_t stage_bytes = las_stage_bytes(rec_bytes, LAS_TILE);
+    const uint32_t sm_stage = smem_u32(smem_raw);
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+    const long long nb = (n + LAS_TILE - 1) / LAS_TILE;
+    const long long b0 = nb * blockIdx.x / gridDim.x, b1 = nb * (blockIdx.x + 1) / gridDim.x;
+    const int my_batches = (int)(b1 - b0);
+    auto batch_points = [&](int k) -> uint32_t {
+        const long long left = n - (b0 + k) * LAS_TILE;
+        return left < LAS_TILE ? (uint32_t)left : (uint32_t)LAS_TILE;
+    };
+    auto load = [&](int k, uint32_t buf) {
+        bulk_load(smem_raw + buf * stage_bytes, recs + (size_t)(b0 + k) * LAS_TILE * rec_bytes,
+                  (batch_points(k) * rec_bytes + 15u) & ~15u, &s_bar[buf]);
+    };
+    if (tid == 0 && my_batches > 0) load(0, 0);
+    for (int k = 0; k < my_batches; ++k) {
+        const uint32_t buf = (uint32_t)k & 1u;
+        if (tid == 0 && k + 1 < my_batches) load(k + 1, buf ^ 1u);
+        const uint32_t npts = batch_points(k);
+        mbar_wait(&s_bar[buf], ((uint32_t)k >> 1) & 1u);
+        float4 *dst = out + (b0 + k) * LAS_TILE;
+#pragma unroll
+        for (int j = 0; j < LAS_TILE / LAS_THREADS; ++j) {
+            const uint32_t i = (uint32_t)(j * LAS_THREADS + tid);
+            if (i < npts) __stcs(dst + i, las_decode_record(sm_stage + buf * stage_bytes + i * rec_bytes, xf));
+        }
+        __syncthreads();            // everybody is done with this buffer before it is refilled
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -735,6 +821,8 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     uint32_t *a_minz = acc + plane_of(MASK, M_MINZ) * cells;   // holds max(256 - zq): 0 = empty
     uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
     __shared__ uint32_t s_ovf;
+    __shared__ float s_div255[256];                      // u8 / 255 (one IEEE division each): the proj values
+    if (out.proj) for (int i = tid; i < 256; i += RED_THREADS) s_div255[i] = __fdiv_rn((float)i, 255.0f);
     auto zero_tile = [&]() {
         uint4 *a4 = reinterpret_cast<uint4 *>(acc);
         const int n4 = NW * cells / 4;
@@ -783,6 +871,10 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         const bool full_w = ncols == TILE_W;
         const bool img_fast = full_w && (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(out.image) & 3) == 0;
         const bool c16_fast = full_w && (kp.W & 1) == 0 && (reinterpret_cast<uintptr_t>(out.count16) & 3) == 0;
+        // proj planes: [C][oH][W], or [B][C][bH][W] for a batched call (a tile never straddles two samples)
+        const size_t pstride = kp.bH ? (size_t)kp.bH * kp.W : gcells;
+        const size_t pbase = kp.bH ? (size_t)(orow0 / kp.bH) * (size_t)(nch - 1) * pstride : 0;
+        const bool proj_fast = full_w && (kp.W & 3) == 0 && (reinterpret_cast<uintptr_t>(out.proj) & 15) == 0;
         bool overflow = false;
         for (int g = tid; g < cells / 4; g += RED_THREADS) {
             const int lr = g >> (TILE_W_LOG2 - 2), lc0 = (g & (TILE_W / 4 - 1)) << 2;
@@ -869,9 +961,15 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             }
             if (out.proj) {
                 for (int c = 0; c < nch; ++c) {
-                    float *dst = out.proj + (size_t)c * gcells + grow;
-                    for (int e = 0; e < 4; ++e)
-                        if (lc0 + e < ncols) dst[e] = __fdiv_rn((float)((pk[e] >> (8 * c)) & 0xFFu), 255.0f);
+                    float *dst = out.proj + pbase + (size_t)c * pstride + grow;
+                    if (proj_fast) {
+                        *reinterpret_cast<float4 *>(dst) =
+                            make_float4(s_div255[(pk[0] >> (8 * c)) & 0xFFu], s_div255[(pk[1] >> (8 * c)) & 0xFFu],
+                                        s_div255[(pk[2] >> (8 * c)) & 0xFFu], s_div255[(pk[3] >> (8 * c)) & 0xFFu]);
+                    } else {
+                        for (int e = 0; e < 4; ++e)
+                            if (lc0 + e < ncols) dst[e] = s_div255[(pk[e] >> (8 * c)) & 0xFFu];
+                    }
                 }
             }
         }
@@ -957,15 +1055,27 @@ int pick_mask(int need, bool count16) {
         if ((m & need) == need && !(count16 && popc6(m) < 2)) return m;
     return M_ALL;
 }
+int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
 // tile height: 128 rows for a single plane, else 64 rows (two reduce CTAs per SM up to 3 planes,
-// so that one tile's finish/write pass overlaps the other's streaming; one CTA per SM beyond)
-int tile_h_log2_for(int mask) {
+// so that one tile's finish/write pass overlaps the other's streaming; one CTA per SM beyond).
+// A small raster (one 1152^2 crop = 81 tiles of 128 rows) takes shorter tiles so that the
+// persistent reduce CTAs of every SM get a few tiles each.
+int tile_h_log2_for(int mask, int height, int width) {
     const int nw = popc6(mask);
     if (const char *e = getenv("LM_BEV_TILE_H_LOG2")) {      // tuning knob (5..7); must keep NW planes <= 227 KB
         const int v = atoi(e);
         if (v >= 5 && v <= 7 && nw * (128 << v) * 4 <= 200 * 1024) return v;
     }
-    return nw <= 1 ? 7 : 6;      // 128 x 64 tiles: 2 CTAs/SM up to 3 planes, 1 CTA/SM (<= 192 KB) up to 6
+    int th = nw <= 1 ? 7 : 6;      // 128 x 64 tiles: 2 CTAs/SM up to 3 planes, 1 CTA/SM (<= 192 KB) up to 6
+    const long long tiles_x = (width + TILE_W - 1) >> TILE_W_LOG2;
+    const long long want = 4ll * sm_count();
+    while (th > 5 && tiles_x * ((height + (1 << th) - 1) >> th) < want) --th;
+    return th;
 }
 
 int validate(const lm_bev_params *p) {
@@ -1013,6 +1123,7 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     k.oH = p->height;
     k.orow = 0;
     k.band = 0;
+    k.bH = 0;
     return k;
 }
 
@@ -1117,12 +1228,6 @@ cudaError_t launch_reduce_mask(int mask, const KParams &kp, const Ws &ws, const 
     }
 }
 
-int sm_count() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms > 0 ? sms : 148;
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1146,7 +1251,7 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
         const bool want16 = out->count16_dev != nullptr;
         const bool banded = out->acc_dev != nullptr && out->acc_band > 0 &&
                             (out->image_dev || out->count16_dev || out->proj_dev);
-        th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16));
+        th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16), p->height, p->width);
     }
     KParams k = make_kparams(p, th);
     if (algo == LM_ALGO_BINNED) {          // a raster with too many tiles runs as row windows: size for one window
@@ -1169,9 +1274,21 @@ int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_
                                    LM_STAGE_ALL);
 }
 
+static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
+                          void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream,
+                          int stages, bool keep_stats, const LasXform *las = nullptr);
+
 int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
                             void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream,
                             int stages) {
+    return rasterize_impl(p, points_dev, n_points, algo, workspace_dev, workspace_bytes, out, stream, stages, false);
+}
+
+// keep_stats: lm_bev_stats keeps accumulating (a batched call that runs sample by sample)
+// las: points_dev is the point-data block of a LAS file, decoded inside bin_points (lm_bev_rasterize_las)
+static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
+                          void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream,
+                          int stages, bool keep_stats, const LasXform *las) {
     int rc = validate(p);
     if (rc) return rc;
     if (n_points < 0 || (n_points > 0 && !points_dev)) return fail(LM_ERR_INVALID, "points_dev is NULL");
@@ -1220,7 +1337,7 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
     // channels need and also emits them raw for the band tiles; acc_band <= 0 accumulates all six planes
     const bool banded = out->acc_dev != nullptr && out->acc_band > 0 && (o.image || o.count16 || o.proj);
     const int mask = pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16);
-    const int th = tile_h_log2_for(mask);
+    const int th = tile_h_log2_for(mask, p->height, p->width);
     const int wrows = window_rows(p, th);
     if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: more than %d tiles per tile row", max_tiles());
     const int n_win = (p->height + wrows - 1) / wrows;
@@ -1257,10 +1374,25 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
         cudaError_t e = cudaSuccess;
         if (stages & LM_STAGE_BIN) {
             // stats (first 64 bytes) accumulate over the windows; everything else restarts
-            const size_t skip = win == 0 ? 0 : L.off_ctl;
+            const size_t skip = win == 0 && !keep_stats ? 0 : L.off_ctl;
             e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
             if (e != cudaSuccess) return cuda_fail(e, "memset");
-            if (n_points > 0) {
+            if (n_points > 0 && las) {
+                const size_t smem = 2 * (size_t)las_stage_bytes((uint32_t)las->record_length, BIN_BATCH) + (size_t)kp.T * 4 * (1 + NSLOT);
+                if (smem > 220 * 1024)
+                    return fail(LM_ERR_UNSUPPORTED, "%d-byte records x %d tiles do not fit in shared memory: use lm_las_decode first",
+                                las->record_length, kp.T);
+                e = cudaFuncSetAttribute(bin_points_las_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return cuda_fail(e, "bin_points_las smem attribute");
+                int occ = 1;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_las_kernel, BIN_THREADS, smem);
+                if (e != cudaSuccess) return cuda_fail(e, "bin_points_las occupancy");
+                long long grid = (long long)sms * (occ < 1 ? 1 : occ);
+                if (grid > bin_ctas_bound(kp.T)) grid = bin_ctas_bound(kp.T);
+                const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
+                if (grid > nb) grid = nb;
+                bin_points_las_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, *las, reinterpret_cast<const unsigned char *>(points_dev), n_points, ws);
+            } else if (n_points > 0) {
                 const size_t smem = bin_smem_bytes(kp.T);
                 e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
@@ -1282,6 +1414,220 @@ int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
         if (!(stages & LM_STAGE_REDUCE)) continue;
+        e = launch_reduce_mask(mask, kp, ws, o, sms, st);
+        if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles launch");
+    }
+    return LM_OK;
+}
+
+// ---- LAS front end (include/lm_las.h)
+namespace {
+int las_xform(const lm_las_xform *x, LasXform *o) {
+    if (!x) return fail(LM_ERR_INVALID, "lm_las_xform is NULL");
+    if (x->record_length < 14 || x->record_length > 100)
+        return fail(LM_ERR_INVALID, "record_length %d outside 14..100", x->record_length);
+    for (int k = 0; k < 3; ++k) {
+        o->scale[k] = x->scale[k]; o->offset[k] = x->offset[k];
+        o->read_offset[k] = x->las_read_offset[k]; o->t[k] = x->translation[k];
+    }
+    for (int k = 0; k < 9; ++k) o->m[k] = x->rot[k];
+    o->record_length = x->record_length;
+    return LM_OK;
+}
+}  // namespace
+
+int lm_las_decode(const uint8_t *records_dev, int64_t n_points, const lm_las_xform *x, float *points_dev, void *stream) {
+    LasXform xf;
+    int rc = las_xform(x, &xf);
+    if (rc) return rc;
+    if (n_points < 0 || (n_points > 0 && (!records_dev || !points_dev))) return fail(LM_ERR_INVALID, "records_dev/points_dev is NULL");
+    if ((reinterpret_cast<uintptr_t>(records_dev) & 15) || (reinterpret_cast<uintptr_t>(points_dev) & 15))
+        return fail(LM_ERR_INVALID, "records_dev and points_dev must be 16-byte aligned");
+    if (n_points == 0) return LM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = 2 * (size_t)las_stage_bytes((uint32_t)xf.record_length, LAS_TILE);
+    cudaError_t e = cudaFuncSetAttribute(las_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "las_decode smem attribute");
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, las_decode_kernel, LAS_THREADS, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "las_decode occupancy");
+    long long grid = (long long)sm_count() * (occ < 1 ? 1 : occ);
+    const long long nb = (n_points + LAS_TILE - 1) / LAS_TILE;
+    if (grid > nb) grid = nb;
+    las_decode_kernel<<<(int)grid, LAS_THREADS, smem, st>>>(xf, records_dev, n_points, reinterpret_cast<float4 *>(points_dev));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "las_decode launch");
+}
+
+int lm_bev_rasterize_las(const lm_bev_params *p, const uint8_t *records_dev, int64_t n_points, const lm_las_xform *x,
+                         void *workspace_dev, size_t workspace_bytes, const lm_bev_outputs *out, void *stream) {
+    LasXform xf;
+    int rc = las_xform(x, &xf);
+    if (rc) return rc;
+    return rasterize_impl(p, reinterpret_cast<const float *>(records_dev), n_points, LM_ALGO_BINNED, workspace_dev,
+                          workspace_bytes, out, stream, LM_STAGE_ALL, false, &xf);
+}
+
+// ---- batched call: up to MAX_BATCH equally-shaped samples per launch set, stacked along the rows
+namespace {
+// samples per launch set: bounded by the batch table, by the tiles one launch handles and (for the
+// stacked u32 cell indices of the outputs) by nothing else; 0 = cannot batch (sample too big)
+int batch_group(const lm_bev_params *p, int th, int n_samples) {
+    const long long tiles = (long long)((p->width + TILE_W - 1) >> TILE_W_LOG2) * ((p->height + (1 << th) - 1) >> th);
+    long long g = max_tiles() / tiles;
+    if (g > MAX_BATCH) g = MAX_BATCH;
+    if (g > n_samples) g = n_samples;
+    if ((long long)p->height * g >= (1ll << 24)) g = ((1ll << 24) - 1) / p->height;
+    return (int)g;
+}
+int batch_tile_h(const lm_bev_params *p, int mask, int n_samples) {
+    // the tile height is picked for the stacked raster; a tile must not straddle two samples
+    const long long stacked = (long long)p->height * (n_samples < MAX_BATCH ? n_samples : MAX_BATCH);
+    int th = tile_h_log2_for(mask, (int)(stacked < (1 << 24) ? stacked : (1 << 24) - 1), p->width);
+    while (th > 5 && (p->height & ((1 << th) - 1))) --th;
+    return th;
+}
+}  // namespace
+
+int lm_bev_workspace_bytes_batch(const lm_bev_params *p, int32_t n_samples, int64_t n_points_total,
+                                 const lm_bev_outputs *out, size_t *bytes) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!bytes || n_points_total < 0 || n_samples < 1) return fail(LM_ERR_INVALID, "bytes is NULL, n_points_total < 0 or n_samples < 1");
+    if (!out) return fail(LM_ERR_INVALID, "out is NULL (the batched call sizes its tiles for the output set)");
+    const bool want16 = out->count16_dev != nullptr;
+    const int mask = pick_mask(needed_mask(p, want16, false), want16);
+    const int th = batch_tile_h(p, mask, n_samples);
+    if (p->height & ((1 << th) - 1)) {        // samples are rasterised one by one through lm_bev_rasterize
+        return lm_bev_workspace_bytes(p, n_points_total, LM_ALGO_BINNED, out, bytes);
+    }
+    const int g = batch_group(p, th, n_samples);
+    if (g < 1) return lm_bev_workspace_bytes(p, n_points_total, LM_ALGO_BINNED, out, bytes);
+    lm_bev_params ps = *p;
+    ps.height = p->height * g;
+    Layout L;
+    rc = make_layout(&ps, n_points_total, LM_ALGO_BINNED, make_kparams(&ps, th).T, &L);
+    if (rc) return rc;
+    *bytes = L.total;
+    return LM_OK;
+}
+
+int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_bev_sample_geom *geoms,
+                           const float *const *points_dev, const int64_t *n_points, void *workspace_dev,
+                           size_t workspace_bytes, const lm_bev_outputs *out, void *stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (n_samples < 1 || !geoms || !points_dev || !n_points) return fail(LM_ERR_INVALID, "n_samples < 1 or a NULL table");
+    if (!out || (!out->image_dev && !out->count16_dev && !out->proj_dev))
+        return fail(LM_ERR_INVALID, "no output buffer requested (image, count16 or proj)");
+    if (out->acc_dev) return fail(LM_ERR_UNSUPPORTED, "raw accumulators are not available from the batched call");
+    if (!workspace_dev || (reinterpret_cast<uintptr_t>(workspace_dev) & 255))
+        return fail(LM_ERR_WORKSPACE, "workspace_dev is NULL or not 256-byte aligned");
+    int64_t total = 0;
+    for (int s = 0; s < n_samples; ++s) {
+        if (n_points[s] < 0 || (n_points[s] > 0 && !points_dev[s])) return fail(LM_ERR_INVALID, "sample %d: points_dev is NULL", s);
+        if (reinterpret_cast<uintptr_t>(points_dev[s]) & 15) return fail(LM_ERR_INVALID, "sample %d: points_dev must be 16-byte aligned", s);
+        if (n_points[s] >= (1ll << 32) - BIN_BATCH) return fail(LM_ERR_UNSUPPORTED, "sample %d: more than 2^32 points", s);
+        const long long lim = 1ll << 24;
+        const long long r0 = geoms[s].row0 < 0 ? -(long long)geoms[s].row0 : geoms[s].row0;
+        const long long c0 = geoms[s].col0 < 0 ? -(long long)geoms[s].col0 : geoms[s].col0;
+        if (r0 + p->height >= lim || c0 + p->width >= lim) return fail(LM_ERR_INVALID, "sample %d: window exceeds the exact-float index range 2^24", s);
+        total += n_points[s];
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char *w = static_cast<unsigned char *>(workspace_dev);
+    const int sms = sm_count();
+    const bool want16 = out->count16_dev != nullptr;
+    const int mask = pick_mask(needed_mask(p, want16, false), want16);
+    const int th = batch_tile_h(p, mask, n_samples);
+    const int group = (p->height & ((1 << th) - 1)) ? 0 : batch_group(p, th, n_samples);
+    const size_t cells = (size_t)p->height * p->width;
+    if (group < 1) {
+        // shapes the stacked raster cannot take (height not a multiple of the tile height, or one
+        // sample already needs row windows): one ordinary call per sample, same results
+        for (int s = 0; s < n_samples; ++s) {
+            lm_bev_params ps = *p;
+            ps.bev_img_offset[0] = geoms[s].bev_img_offset[0];
+            ps.bev_img_offset[1] = geoms[s].bev_img_offset[1];
+            ps.local_min_ele = geoms[s].local_min_ele;
+            ps.row0 = geoms[s].row0;
+            ps.col0 = geoms[s].col0;
+            lm_bev_outputs os = *out;
+            if (os.image_dev) os.image_dev += (size_t)s * cells * p->n_channels;
+            if (os.count16_dev) os.count16_dev += (size_t)s * cells;
+            if (os.proj_dev) os.proj_dev += (size_t)s * cells * p->n_channels;
+            rc = rasterize_impl(&ps, points_dev[s], n_points[s], LM_ALGO_BINNED, workspace_dev, workspace_bytes, &os, stream,
+                                LM_STAGE_ALL, s > 0);
+            if (rc) return rc;
+        }
+        return LM_OK;
+    }
+    for (int s0 = 0; s0 < n_samples; s0 += group) {
+        const int nb = n_samples - s0 < group ? n_samples - s0 : group;
+        lm_bev_params ps = *p;
+        ps.height = p->height * nb;
+        ps.row0 = 0;
+        ps.col0 = 0;
+        KParams kp = make_kparams(&ps, th);
+        kp.bH = p->height;
+        BatchTab bt;
+        memset(&bt, 0, sizeof(bt));
+        bt.nb = nb;
+        bt.bH = p->height;
+        int64_t gpts = 0;
+        uint32_t batches = 0;
+        for (int s = 0; s < nb; ++s) {
+            bt.pts[s] = reinterpret_cast<const float4 *>(points_dev[s0 + s]);
+            bt.first[s] = batches;
+            bt.count[s] = (uint32_t)n_points[s0 + s];
+            batches += (uint32_t)((n_points[s0 + s] + BIN_BATCH - 1) / BIN_BATCH);
+            bt.off0[s] = geoms[s0 + s].bev_img_offset[0];
+            bt.off1[s] = geoms[s0 + s].bev_img_offset[1];
+            bt.zmin[s] = geoms[s0 + s].local_min_ele;
+            bt.row0[s] = geoms[s0 + s].row0;
+            bt.col0[s] = geoms[s0 + s].col0;
+            gpts += n_points[s0 + s];
+        }
+        for (int s = nb; s <= MAX_BATCH; ++s) bt.first[s] = batches;
+        Layout L;
+        rc = make_layout(&ps, total, LM_ALGO_BINNED, kp.T, &L);      // sized like lm_bev_workspace_bytes_batch
+        if (rc) return rc;
+        if (workspace_bytes < L.total) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, L.total);
+        Ws ws;
+        ws.stats = reinterpret_cast<lm_bev_stats *>(w);
+        ws.ctl = reinterpret_cast<Ctl *>(w + L.off_ctl);
+        ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
+        ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
+        ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
+        ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
+        ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
+        ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
+        ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
+        ws.acc = nullptr;
+        ws.pool_chunks = L.pool_chunks;
+        const size_t skip = s0 == 0 ? 0 : L.off_ctl;             // stats accumulate over the launch sets
+        cudaError_t e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+        if (batches > 0) {
+            const size_t smem = bin_smem_bytes(kp.T);
+            e = cudaFuncSetAttribute(bin_points_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
+            int occ = 1;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_batch_kernel, BIN_THREADS, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
+            long long grid = (long long)sms * (occ < 1 ? 1 : occ);
+            if (grid > bin_ctas_bound(kp.T)) grid = bin_ctas_bound(kp.T);
+            if (grid > (long long)batches) grid = batches;
+            bin_points_batch_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, bt, ws);
+        }
+        scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
+        if (batches > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
+        Outs o = {out->image_dev, out->count16_dev, out->proj_dev, nullptr, 0};
+        if (o.image) o.image += (size_t)s0 * cells * p->n_channels;
+        if (o.count16) o.count16 += (size_t)s0 * cells;
+        if (o.proj) o.proj += (size_t)s0 * cells * p->n_channels;
         e = launch_reduce_mask(mask, kp, ws, o, sms, st);
         if (e != cudaSuccess) return cuda_fail(e, "reduce_tiles launch");
     }

@@ -98,3 +98,15 @@ def write_las(path: str, xyz: np.ndarray, intensity: np.ndarray, scale=(0.001, 0
     with open(path, "wb") as f:
         f.write(bytes(head))
         f.write(rec.tobytes())
+
+
+def read_point_block(path: str):
+    """-> (uint8 [n_points * record_length] exactly as on disk, header): the input of the GPU
+    decode (``bev.decode_las`` / ``BevRasterizer.rasterize_las``); nothing is scaled on the host."""
+    with open(path, "rb") as f:
+        hdr = read_header(f.read(375))
+        f.seek(hdr.offset_to_points)
+        raw = np.fromfile(f, dtype=np.uint8, count=hdr.n_points * hdr.record_length)
+    if raw.size != hdr.n_points * hdr.record_length:
+        raise ValueError(f"{path}: truncated point data")
+    return raw, hdr

@@ -37,7 +37,8 @@ class BatchProjector:
                        ele_reso=g[5], channels=self.channels, row0=row0, col0=col0)
 
     def __call__(self, points: List[torch.Tensor], geoms=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        from .bev import BevRasterizer
+        """One batched C-ABI call (``lm_bev_rasterize_batch``): the B clouds share one set of launches."""
+        from .bev import BatchRasterizer
         B = len(points)
         dev = points[0].device
         if dev.type != "cuda":
@@ -45,17 +46,18 @@ class BatchProjector:
         C = len(self.channels)
         if out is None:
             out = torch.empty((B, C, self.tile, self.tile), dtype=torch.float32, device=dev)
-        for b in range(B):
-            spec = self.spec_for(None if geoms is None else geoms[b])
-            n = int(points[b].shape[0])
-            key = (spec, dev)
-            r = self._rasters.get(key)
-            if r is None or r.max_points < n:
-                r = BevRasterizer(spec, max(n, 1), device=dev, outputs=("proj",))
-                if len(self._rasters) > 64:
-                    self._rasters.clear()
-                self._rasters[key] = r
-            r(points[b].contiguous(), out={"proj": out[b]})
+        specs = [self.spec_for(None if geoms is None else geoms[b]) for b in range(B)]
+        common = replace(specs[0], bev_img_offset=(0.0, 0.0), local_min_ele=0.0, row0=0, col0=0)
+        pts = [p.contiguous() for p in points]
+        total = sum(int(p.shape[0]) for p in pts)
+        key = (common, dev, B)
+        r = self._rasters.get(key)
+        if r is None or r.max_points_total < total:
+            if len(self._rasters) > 16:
+                self._rasters.clear()
+            r = BatchRasterizer(common, B, max(total, 1), device=dev, outputs=("proj",))
+            self._rasters[key] = r
+        r(pts, specs, out={"proj": out})
         return out
 
 

@@ -12,9 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "lm_bev.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lm_bev_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(os.listdir(inc)):
+        if not h.endswith(".h"):
+            continue
+        text = open(os.path.join(inc, h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(lm_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_exported_and_bound(native_lib):
@@ -30,6 +36,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_cabi.LmBevParams) == 4 * 4 + 4 * 4 + 2 * 4 + 2 * 4 + 4 + 4 * 4   # 68 bytes, no padding
     assert C.sizeof(_cabi.LmBevOutputs) == 4 * 8 + 8
     assert C.sizeof(_cabi.LmBevStats) == 32 and _cabi.LmBevStats.n_valid.offset == 8
+    assert C.sizeof(_cabi.LmBevSampleGeom) == 24
+    assert C.sizeof(_cabi.LmLasXform) == 8 + 21 * 8 and _cabi.LmLasXform.rot.offset == 8 + 12 * 8
 
 
 def test_workspace_bytes_and_argument_errors(native_lib):
@@ -83,3 +91,23 @@ def test_product_path_has_no_cpu_fallback():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
     with pytest.raises(RuntimeError, match="CUDA"):
         bev.BevRasterizer(BevSpec(8, 8), 16, device="cpu")
+
+
+def test_batch_and_las_argument_errors(native_lib):
+    """The newer entry points reject bad arguments before any launch (no GPU needed)."""
+    spec = BevSpec(1152, 1152)
+    p = _cabi.make_params(spec)
+    out = C.c_size_t(0)
+    o = _cabi.LmBevOutputs()
+    o.proj_dev = 1
+    assert native_lib.lm_bev_workspace_bytes_batch(C.byref(p), 8, 80_000_000, C.byref(o), C.byref(out)) == 0
+    assert out.value % 256 == 0 and out.value > 80_000_000 * 4
+    assert native_lib.lm_bev_workspace_bytes_batch(C.byref(p), 0, 10, C.byref(o), C.byref(out)) == -1
+    assert native_lib.lm_bev_workspace_bytes_batch(C.byref(p), 8, 10, None, C.byref(out)) == -1
+    x = _cabi.make_las_xform(10, (0.001,) * 3, (0.0,) * 3)
+    assert native_lib.lm_las_decode(None, 0, C.byref(x), None, None) == -1
+    assert b"record_length" in native_lib.lm_bev_last_error()
+    x = _cabi.make_las_xform(20, (0.001,) * 3, (0.0,) * 3)
+    assert native_lib.lm_las_decode(None, 0, C.byref(x), None, None) == 0          # nothing to do
+    assert native_lib.lm_las_decode(None, 5, C.byref(x), None, None) == -1
+    assert native_lib.lm_las_decode(None, 0, None, None, None) == -1
