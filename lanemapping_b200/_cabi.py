@@ -57,6 +57,23 @@ class LmLasXform(C.Structure):
     ]
 
 
+class LmImg2PcParams(C.Structure):
+    _fields_ = [
+        ("img_reso", C.c_double * 2), ("bev_img_offset", C.c_double * 2),
+        ("ele_reso", C.c_double), ("local_min_ele", C.c_double),
+        ("translation", C.c_double * 3), ("quat", C.c_double * 4), ("quat_inv", C.c_double * 4),
+        ("las_read_offset", C.c_double * 3),
+    ]
+
+
+class LmJitter(C.Structure):
+    _fields_ = [("order", C.c_int32 * 4), ("brightness", C.c_float), ("contrast", C.c_float),
+                ("saturation", C.c_float), ("reserved", C.c_float)]
+
+
+JITTER_PARTIALS = 64
+
+
 class LmBevStats(C.Structure):
     _fields_ = [
         ("error", C.c_uint32), ("n_chunks", C.c_uint32),
@@ -82,6 +99,13 @@ SYMBOLS = {
     "lm_las_decode": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(LmLasXform), C.c_void_p, C.c_void_p]),
     "lm_bev_rasterize_las": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.POINTER(LmLasXform), C.c_void_p,
                                        C.c_size_t, C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_bev_img2pc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lm_label_endpoint_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "lm_label_polylines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lm_proj_color_jitter": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(LmJitter), C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p]),
     "lm_bev_acc_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "lm_bev_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32,
                                   C.POINTER(LmBevOutputs), C.c_void_p]),

@@ -22,6 +22,7 @@
 #include "lm_bev.h"
 #include "lm_las.h"
 #include "lm_dev.cuh"
+#include "lm_host.h"
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -29,6 +30,24 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+namespace {
+extern thread_local char g_err[512];
+}
+// shared with the other translation units of the library (csrc/lm_host.h)
+int lm_fail_msg(int code, const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int lm_cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+int lm_sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
 
 namespace {
 
@@ -126,10 +145,7 @@ int fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
-int cuda_fail(cudaError_t e, const char *what) {
-    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
-    return (int)e;
-}
+int cuda_fail(cudaError_t e, const char *what) { return lm_cuda_fail(e, what); }
 
 // ------------------------------------------------------------------------------------------
 // per-point quantisation (the spec; oracle/bev_oracle.py::quantise_points restates it)
@@ -729,20 +745,20 @@ __device__ __forceinline__ void store_pixels4(uint8_t *dst, const uint32_t pk[4]
 }
 
 // count and one sum share a word [count:12 | sum:20] when PACKED: one atomic instead of two (the
-// kernel is bound by shared-memory atomic wavefronts).  sum <= 255 * count < 2^20 while count < 4096;
-// the add that would wrap the count field is seen through the returned old value (*ovf), and the
-// tile is then redone unpacked -- exact for any input.
+// kernel is bound by shared-memory atomic wavefronts).  sum <= 255 * count < 2^20 while count < 4096.
+// Nothing is returned by the atomics (no scoreboard wait on the hot path); a wrapped count field is
+// found afterwards by conservation -- the counts of a tile's cells must add up to the records
+// streamed into it, and a wrap loses 4096 -- and the tile is then redone unpacked: exact for any input.
 constexpr uint32_t PK_SHIFT = 20, PK_SUM_MASK = (1u << PK_SHIFT) - 1u, PK_CNT_MAX = (1u << (32 - PK_SHIFT)) - 1u;
 
 template <int MASK, bool PACKED>
 __device__ __forceinline__ void accumulate_rec(uint32_t rec, uint32_t *a_cnt, uint32_t *a_sumi, uint32_t *a_sumz,
-                                               uint32_t *a_maxi, uint32_t *a_minz, uint32_t *a_maxz, uint32_t *ovf) {
+                                               uint32_t *a_maxi, uint32_t *a_minz, uint32_t *a_maxz) {
     const uint32_t cell = rec >> 16, iq = (rec >> 8) & 0xFFu, zq = rec & 0xFFu;
     constexpr bool PACK_Z = PACKED && (MASK & M_SUMZ);            // partner of the count: sum_z if tracked, else sum_i
     constexpr bool PACK_I = PACKED && !(MASK & M_SUMZ) && (MASK & M_SUMI);
     if (PACK_Z || PACK_I) {
-        const uint32_t old = atomicAdd(&a_cnt[cell], (1u << PK_SHIFT) | (PACK_Z ? zq : iq));
-        if ((old >> PK_SHIFT) == PK_CNT_MAX) *ovf = 1u;
+        atomicAdd(&a_cnt[cell], (1u << PK_SHIFT) | (PACK_Z ? zq : iq));
     } else if (MASK & M_CNT) {
         atomicAdd(&a_cnt[cell], 1u);
     }
@@ -756,9 +772,10 @@ __device__ __forceinline__ void accumulate_rec(uint32_t rec, uint32_t *a_cnt, ui
 // stream one tile's chunks: one chunk per warp and iteration, coalesced uint4 loads with the next
 // chunk's index entry and records fetched while the current ones are reduced
 template <int MASK, bool PACKED>
-__device__ __forceinline__ void stream_tile(const Ws &ws, const uint32_t *my_index, uint32_t nchunks, int warp, int lane,
-                                            uint32_t *a_cnt, uint32_t *a_sumi, uint32_t *a_sumz, uint32_t *a_maxi,
-                                            uint32_t *a_minz, uint32_t *a_maxz, uint32_t *ovf) {
+__device__ __forceinline__ uint32_t stream_tile(const Ws &ws, const uint32_t *my_index, uint32_t nchunks, int warp, int lane,
+                                                uint32_t *a_cnt, uint32_t *a_sumi, uint32_t *a_sumz, uint32_t *a_maxi,
+                                                uint32_t *a_minz, uint32_t *a_maxz) {
+    uint32_t streamed = 0;                                       // records this warp reduced (warp-uniform)
     constexpr int V = PIECE_RECS / 128;                          // uint4 loads per lane per piece
     constexpr int NWARPS = RED_THREADS / 32;
     constexpr uint32_t ID_MASK = (1u << IDX_ID_BITS) - 1u;
@@ -772,26 +789,39 @@ __device__ __forceinline__ void stream_tile(const Ws &ws, const uint32_t *my_ind
         for (int q = 0; q < V; ++q)
             if ((uint32_t)((q * 32 + lane) * 4) < cnt) v[q] = __ldcs(src + q * 32 + lane);
     }
+    // pieces further ahead are pulled into L2 with a bulk prefetch (no registers, one lane): the
+    // register prefetch above only covers one piece of work, less than an HBM round trip under load
+    auto l2_prefetch = [&](uint32_t ci) {
+        if (lane == 0 && ci < nchunks) {
+            const uint32_t e = __ldg(my_index + ci);
+            const uint32_t bytes = ((((e >> IDX_ID_BITS) + 1u) * 4u) + 15u) & ~15u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ws.pool + (size_t)(e & ID_MASK) * PIECE_RECS), "r"(bytes) : "memory");
+        }
+    };
+    l2_prefetch(c + NWARPS);
+    l2_prefetch(c + 2 * NWARPS);
     while (c < nchunks) {
         const uint32_t cnt = (ent >> IDX_ID_BITS) + 1u;
         const uint32_t cn = c + NWARPS;
         const uint32_t ent_next = cn < nchunks ? __ldg(my_index + cn) : 0u;
+        l2_prefetch(c + 3 * NWARPS);
+        streamed += cnt;
         if (cnt == PIECE_RECS) {                 // full piece: no per-record bounds checks
 #pragma unroll
             for (int q = 0; q < V; ++q) {
-                accumulate_rec<MASK, PACKED>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
-                accumulate_rec<MASK, PACKED>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
-                accumulate_rec<MASK, PACKED>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
-                accumulate_rec<MASK, PACKED>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                accumulate_rec<MASK, PACKED>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                accumulate_rec<MASK, PACKED>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                accumulate_rec<MASK, PACKED>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                accumulate_rec<MASK, PACKED>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
             }
         } else {
 #pragma unroll
             for (int q = 0; q < V; ++q) {
                 const uint32_t i0 = (uint32_t)((q * 32 + lane) * 4);
-                if (i0 + 0 < cnt) accumulate_rec<MASK, PACKED>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
-                if (i0 + 1 < cnt) accumulate_rec<MASK, PACKED>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
-                if (i0 + 2 < cnt) accumulate_rec<MASK, PACKED>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
-                if (i0 + 3 < cnt) accumulate_rec<MASK, PACKED>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, ovf);
+                if (i0 + 0 < cnt) accumulate_rec<MASK, PACKED>(v[q].x, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                if (i0 + 1 < cnt) accumulate_rec<MASK, PACKED>(v[q].y, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                if (i0 + 2 < cnt) accumulate_rec<MASK, PACKED>(v[q].z, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+                if (i0 + 3 < cnt) accumulate_rec<MASK, PACKED>(v[q].w, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
             }
         }
         c = cn;
@@ -804,6 +834,7 @@ __device__ __forceinline__ void stream_tile(const Ws &ws, const uint32_t *my_ind
                 if ((uint32_t)((q * 32 + lane) * 4) < cnt2) v[q] = __ldcs(src + q * 32 + lane);
         }
     }
+    return streamed;
 }
 
 template <int MASK>
@@ -820,7 +851,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     uint32_t *a_maxi = acc + plane_of(MASK, M_MAXI) * cells;
     uint32_t *a_minz = acc + plane_of(MASK, M_MINZ) * cells;   // holds max(256 - zq): 0 = empty
     uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
-    __shared__ uint32_t s_ovf;
+    __shared__ uint32_t s_in, s_cnt;                     // records streamed into / counted in the current tile
     __shared__ float s_div255[256];                      // u8 / 255 (one IEEE division each): the proj values
     if (out.proj) for (int i = tid; i < 256; i += RED_THREADS) s_div255[i] = __fdiv_rn((float)i, 255.0f);
     auto zero_tile = [&]() {
@@ -829,11 +860,10 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         for (int i = tid; i < n4; i += RED_THREADS) a4[i] = make_uint4(0, 0, 0, 0);
     };
     zero_tile();            // the finish pass of every tile leaves the planes zeroed for the next one
-    if (tid == 0) s_ovf = 0;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_tile = (int)atomicAdd(&ws.ctl->tile_counter, 1u);
+        if (tid == 0) { s_tile = (int)atomicAdd(&ws.ctl->tile_counter, 1u); s_in = 0; s_cnt = 0; }
         __syncthreads();
         if (s_tile >= kp.T) break;
         const int t = (int)ws.tile_order[s_tile];               // heaviest tiles first
@@ -850,17 +880,16 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         // ---- stream the tile's chunks with integer atomics in shared memory; count+sum packed in one
         //      word when possible, redone unpacked if a cell's count field overflowed
         constexpr bool CAN_PACK = (MASK & M_CNT) && (MASK & (M_SUMZ | M_SUMI));
-        stream_tile<MASK, CAN_PACK>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, &s_ovf);
-        __syncthreads();
-        const bool packed_ok = CAN_PACK && s_ovf == 0;
-        if (CAN_PACK && !packed_ok) {
-            __syncthreads();                     // everybody has read s_ovf
-            zero_tile();
-            if (tid == 0) s_ovf = 0;
-            __syncthreads();
-            stream_tile<MASK, false>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz, &s_ovf);
-            __syncthreads();
+        for (int round = 0; round < 2; ++round) {                // round 1 only after a wrapped packed count
+        const bool packed_ok = CAN_PACK && round == 0;
+        if (packed_ok) {
+            const uint32_t streamed = stream_tile<MASK, CAN_PACK>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
+            if (lane == 0 && streamed) atomicAdd(&s_in, streamed);
+        } else {
+            stream_tile<MASK, false>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
         }
+        __syncthreads();
+        uint32_t counted = 0;                                    // packed round: sum of this thread's cell counts
 
         // ---- finish + write-out in one pass: every thread takes 4 neighbouring cells of a row (a warp
         //      covers a whole 128-cell tile row), derives the channels, assembles the output words in
@@ -899,6 +928,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
                 if (packed_ok) {                                 // unpack [count:12 | sum:20]
                     if (MASK & M_SUMZ) sz = cnt & PK_SUM_MASK; else si = cnt & PK_SUM_MASK;
                     cnt >>= PK_SHIFT;
+                    counted += cnt;
                 }
                 const uint32_t mi = mi4[e], nzr = nz4[e], xz = xz4[e];
                 const uint32_t nz = nzr ? 256u - nzr : 0u;      // 0 for an empty cell, with or without a count plane
@@ -974,6 +1004,14 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             }
         }
         if (overflow) atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_CELL_OVERFLOW);
+        if (!packed_ok) break;
+        // conservation check of the packed round (block-uniform outcome)
+        for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
+        if (lane == 0 && counted) atomicAdd(&s_cnt, counted);
+        __syncthreads();
+        if (s_cnt == s_in) break;
+        __syncthreads();                                         // every thread has compared before the next round
+        }
     }
 }
 
@@ -1055,11 +1093,7 @@ int pick_mask(int need, bool count16) {
         if ((m & need) == need && !(count16 && popc6(m) < 2)) return m;
     return M_ALL;
 }
-int sm_count() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms > 0 ? sms : 148;
-}
+int sm_count() { return lm_sm_count(); }
 
 // tile height: 128 rows for a single plane, else 64 rows (two reduce CTAs per SM up to 3 planes,
 // so that one tile's finish/write pass overlaps the other's streaming; one CTA per SM beyond).

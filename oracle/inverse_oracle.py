@@ -41,11 +41,14 @@ def fill_empty_elevation(img, roi_pts, roi_len):
 
 
 def least_square(X, Y):
+    """coor_img2pc.py:59-73.  Upstream uses Python's builtin sum(): strictly left-to-right float64
+    additions -- np.sum's pairwise order rounds differently from 8 elements on, so it must not be used
+    here (tests/golden/inverse_io3.npz, random data run through the reference, pins this)."""
     n = len(Y)
-    p = n * np.sum(X * Y) - np.sum(X) * np.sum(Y)
-    q = n * np.sum(X * X) - np.sum(X) * np.sum(X)
+    p = n * sum(X * Y) - sum(X) * sum(Y)
+    q = n * sum(X * X) - sum(X) * sum(X)
     w = 0.0 if abs(q) < EPS else p / q
-    b = np.sum(Y - w * X) / n
+    b = sum(Y - w * X) / n
     return w, b
 
 

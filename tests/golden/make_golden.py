@@ -12,6 +12,11 @@ contracts its in-tree code does fix):
   loader_contract.json                the loader's op sequence (laserlane_proposals.py:87-94) on the PNG
   label_frame.json                    reference data/convert_data.py frame facts (1152 hard-coded tile,
                                       NpEncoder) used by the naming tests
+  inverse_io2.json                    a harder inverse case: vertices inside / on the rim of empty holes
+                                      (in-place hole filling that later vertices see), a non-unit quaternion
+  inverse_io3.npz                     random crops / polylines / poses through the same reference function
+  labels_in.json, labels_*.png        reference data/convert_data.write_instance_orientation_seq run on
+                                      synthetic polylines: the four label rasters it writes
 """
 import json
 import os
@@ -62,6 +67,98 @@ def polylines():
     return seqs, lens
 
 
+def label_inputs():
+    """Polylines (row, col) of a synthetic label crop: crossing lanes (the later one must win), every
+    octant of segment direction incl. right-to-left ones, a degenerate lane, end points inside and
+    outside the 20 px clip border."""
+    lanes = [
+        [(30.0, 200.5), (300.2, 230.7), (700.9, 260.1), (1100.4, 300.8)],           # steep, down the image
+        [(1120.0, 640.0), (800.5, 600.2), (400.1, 655.9), (25.7, 610.3)],           # drawn bottom-up
+        [(500.0, 100.0), (520.3, 500.6), (480.8, 900.2), (510.0, 1130.5)],          # shallow: crosses the others
+        [(10.0, 900.0), (400.0, 905.0), (1145.0, 1140.0)],                           # both end points in the border
+        [(600.0, 50.0), (600.0, 50.0)],                                              # degenerate: no lane instance
+        [(200.0, 1000.0), (200.0, 700.0), (640.0, 700.0), (640.0, 1000.0), (300.0, 1000.0)],   # axis-aligned loop, leftwards runs
+    ]
+    n, m = len(lanes), max(len(l) for l in lanes)
+    seqs = np.zeros((n, m, 2))
+    lens = []
+    for i, l in enumerate(lanes):
+        seqs[i, :len(l)] = l
+        lens.append(len(l))
+    semantic = [1, 2, 1, 3, 1, 2]
+    instance = [1, 2, 3, 4, 5, 6]
+    return seqs, lens, semantic, instance
+
+
+def make_labels(ref_convert):
+    import tempfile
+    import cv2
+    seqs, lens, semantic, instance = label_inputs()
+    orient = ref_convert.cal_seq_orientation(seqs.copy(), lens)          # reference :72-104
+    with tempfile.TemporaryDirectory() as d:
+        names = [os.path.join(d, k) for k in ("seq.json", "sem.png", "ins.png", "ori.png", "endp.png")]
+        ref_convert.write_instance_orientation_seq(seqs.copy(), lens, semantic, instance, orient, *names)   # :319-369
+        for k, src in zip(("semantic", "instance", "orient", "endp"), names[1:]):
+            img = cv2.imread(src, cv2.IMREAD_UNCHANGED)
+            assert img.dtype == np.uint8 and img.shape == (1152, 1152), (img.dtype, img.shape)
+            cv2.imwrite(os.path.join(HERE, f"labels_{k}.png"), img, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+    with open(os.path.join(HERE, "labels_in.json"), "w") as f:
+        json.dump({"seqs": seqs.tolist(), "lens": lens, "semantic": semantic, "instance": instance,
+                   "orient": orient.tolist()}, f)
+
+
+def make_inverse2(io_utils, coor_img2pc, ref_convert):
+    """Second inverse case on the golden crop: polylines through the empty hole (rows/cols 40-59) so that
+    several vertices are filled in place and later searches see the earlier fills; a vertex at (0,0);
+    a non-unit quaternion (the reference divides the conjugate by |q|, not |q|^2)."""
+    from PIL import Image
+    parsed = io_utils.load_pc_2_img_transform_paras(os.path.join(HERE, "golden_crop.txt"))
+    parsed["las_rotation_trans_quan"] = [1.5, -2.25, 0.5, 0.9, 0.1, -0.2, 0.45]
+    seqs = np.zeros((4, 12, 2))
+    lens = [12, 9, 12, 5]
+    seqs[0, :, 0], seqs[0, :, 1] = np.arange(38, 62, 2), np.arange(38, 62, 2) + 0.5      # diagonal through the hole
+    seqs[1, :9, 0], seqs[1, :9, 1] = 49.7, np.arange(36, 63, 3)                          # along a row inside it
+    seqs[2, :, 0], seqs[2, :, 1] = np.arange(44, 56, 1), 50.2                            # dense: neighbours get filled
+    seqs[3, :5, 0], seqs[3, :5, 1] = [0.0, 3.0, 50.0, 120.0, 127.0], [0.0, 3.0, 50.0, 5.0, 127.0]
+    img = Image.open(os.path.join(HERE, "golden_crop.png"))
+    world = coor_img2pc.transform_coordinate_from_img_2_pc(parsed, seqs.copy(), lens, img)
+    filled = coor_img2pc.modify_empty_pixel_elevation(np.array(img), seqs.copy(), lens)
+    changed = np.argwhere(filled[:, :, 1] != np.array(img)[:, :, 1])
+    with open(os.path.join(HERE, "inverse_io2.json"), "w") as f:
+        json.dump({"params": parsed, "img_seqs": seqs.tolist(), "img_seq_lens": lens, "world": world.tolist(),
+                   "filled_px": [[int(r), int(c), int(filled[r, c, 1])] for r, c in changed]}, f, cls=ref_convert.NpEncoder)
+
+
+def make_inverse3(coor_img2pc):
+    """Random crops, random polylines, random poses through the reference: pins the summation order of
+    LeastSuqare (builtin sum) and the hole filling on arbitrary data.  Stored as a compressed npz."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    B, H, W, L, V = 3, 96, 80, 6, 17
+    images = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    images[rng.random((B, H, W)) < 0.6] = 0
+    images[:, 10:40, 20:50] = 0
+    seqs = np.zeros((B, L, V, 2))
+    lens = rng.integers(1, V + 1, (B, L))
+    lens[:, 0] = V
+    poses = np.zeros((B, 13))
+    world = np.zeros((B, L, V, 3))
+    for b in range(B):
+        for l in range(L):
+            seqs[b, l, :lens[b, l], 0] = rng.uniform(0, H - 1e-6, lens[b, l])
+            seqs[b, l, :lens[b, l], 1] = rng.uniform(0, W - 1e-6, lens[b, l])
+        q = rng.normal(size=4)
+        par = {"img_reso": [0.05, 0.04], "bev_img_offset": [float(rng.uniform(-50, 50)), float(rng.uniform(-50, 50))],
+               "ele_reso": 0.05, "local_min_ele": float(rng.uniform(-3, 3)),
+               "las_rotation_trans_quan": [*rng.uniform(-10, 10, 3).tolist(), *(q / np.linalg.norm(q)).tolist()],
+               "las_read_offset": [533000.0, 3380000.0, 20.0]}
+        poses[b] = [*par["bev_img_offset"], par["local_min_ele"], *par["las_rotation_trans_quan"], *par["las_read_offset"]]
+        world[b] = coor_img2pc.transform_coordinate_from_img_2_pc(par, seqs[b].copy(), [int(v) for v in lens[b]],
+                                                                  Image.fromarray(images[b]))
+    np.savez_compressed(os.path.join(HERE, "inverse_io3.npz"), images=images, seqs=seqs, lens=lens.astype(np.int32),
+                        poses=poses, world=world)
+
+
 def main():
     from PIL import Image
     import io_utils                                       # reference baseline/utils/io_utils.py
@@ -104,6 +201,9 @@ def main():
         json.dump({"tile_px_hardcoded": 1152 if "(1152, 1152)" in src else None,
                    "pool_processes": 12 if "num_process = 12" in inspect.getsource(ref_convert.multiprocessing_seqs_files) else None},
                   f, indent=1)
+    make_inverse2(io_utils, coor_img2pc, ref_convert)
+    make_inverse3(coor_img2pc)
+    make_labels(ref_convert)
     print("golden fixtures written to", HERE)
 
 

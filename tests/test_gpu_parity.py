@@ -125,6 +125,28 @@ def test_edge_inputs(bev, algo):
     assert got["image"][7, 9, 2] == 255 and got["count16"][7, 9] == 65535
 
 
+@pytest.mark.parametrize("channels,count16", [(CFG2_CH, False), (CFG4_CH, True), ((CH_MEAN_I,), False)])
+@pytest.mark.parametrize("hot", [4095, 4096, 4097, 8192, 70_000])
+def test_packed_count_wrap_is_found_and_redone(bev, channels, count16, hot):
+    """reduce_tiles packs [count:12 | sum:20] in one word and checks conservation per tile: cells with
+    exactly 4095 points stay packed, 4096 and beyond must trigger the unpacked redo (also several cells
+    wrapping in one tile, and tiles without a wrap next to them)."""
+    spec = BevSpec(200, 300, img_reso=(1.0, 1.0), ele_reso=0.1, channels=channels, count16=count16)
+    rng = np.random.default_rng(hot)
+    bg = np.stack([rng.uniform(0, 200, 40_000), rng.uniform(0, 300, 40_000), rng.uniform(0, 25, 40_000),
+                   rng.uniform(0, 40000, 40_000)], axis=1).astype(np.float32)
+    cells = [(7.5, 9.5), (70.5, 140.5), (71.5, 140.5)] if hot > 4096 else [(7.5, 9.5)]
+    parts = [bg]
+    for k, (x, y) in enumerate(cells):
+        h = np.tile(np.array([[x, y, 1.0, 20000.0]], np.float32), (hot + k, 1))
+        h[:, 2] = rng.uniform(0, 25, hot + k)
+        h[:, 3] = rng.uniform(0, 40000, hot + k)
+        parts.append(h)
+    cloud = np.concatenate(parts)
+    rng.shuffle(cloud)
+    assert_matches_oracle(bev, cloud, spec, "binned")
+
+
 def test_binned_equals_direct_and_is_deterministic(bev):
     spec = BevSpec(1152, 1152, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(1152, 1152)), count16=True)
     cloud = make_cloud(3_000_000, spec, seed=77, order="shuffled")

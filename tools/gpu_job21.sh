@@ -1,0 +1,8 @@
+#!/bin/bash
+# N=2: parity of the conservation-check reduce, NCCL strip test, bench at N=2, single-rank strip step profile
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_strips_nccl.py -x -q 2>&1 | tail -5
+timeout 600 python tools/quick_bench.py --cfg 2 --algos binned --orders scan 2>&1 | grep -v generated
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+cat gpurun_out/bench_n2.json; tail -n 3 gpurun_out/bench_n2.err
+timeout 600 python tools/strip_step_profile.py 2>&1 | tail -3
