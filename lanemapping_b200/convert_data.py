@@ -58,15 +58,18 @@ def plan_raster(xyz_world: np.ndarray, las_read_offset: Sequence[float], pose: S
     params = PcImgParams(coor_las_path, tuple(las_read_offset), tuple(pose), (0.0, 0.0), tuple(img_reso), 0.0,
                          float(ele_reso))
     local = world_to_local(xyz_world, params)
-    lo = local.min(axis=0)
-    hi = local.max(axis=0)
+    spec = plan_from_extent(local.min(axis=0), local.max(axis=0), img_reso, ele_reso, tile, channels, count16)
+    return spec, local, params
+
+
+def plan_from_extent(lo, hi, img_reso, ele_reso, tile, channels, count16) -> BevSpec:
+    """Mosaic of whole tiles covering the local-frame extent [lo, hi] (x, y, z)."""
     off = (float(np.floor(lo[0])), float(np.floor(lo[1])))      # integers: exact in float32
     n_r = max(1, int(np.ceil((hi[0] - off[0]) / img_reso[0] / tile + 1e-9)))
     n_c = max(1, int(np.ceil((hi[1] - off[1]) / img_reso[1] / tile + 1e-9)))
     min_ele = float(np.floor(lo[2] * 10.0) / 10.0)
-    spec = BevSpec(n_r * tile, n_c * tile, bev_img_offset=off, img_reso=tuple(img_reso), local_min_ele=min_ele,
+    return BevSpec(n_r * tile, n_c * tile, bev_img_offset=off, img_reso=tuple(img_reso), local_min_ele=min_ele,
                    ele_reso=float(ele_reso), channels=tuple(channels), count16=count16)
-    return spec, local, params
 
 
 def _stem(seq_id: int, crop_index: int) -> str:
@@ -91,8 +94,13 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
                           img_reso: Tuple[float, float] = (0.05, 0.05), ele_reso: float = 0.05, tile: int = TILE,
                           channels: Sequence[int] = DEFAULT_CHANNELS, count16_dir: Optional[str] = None,
                           pose: Sequence[float] = IDENTITY_POSE, first_index: int = 1, device: str = "cuda",
-                          skip_existing: bool = True, crop_points_dir: Optional[str] = None) -> List[str]:
-    """LAS/NPY cloud -> every non-empty ``tile`` x ``tile`` crop as PNG + sidecar.  Returns the stems."""
+                          skip_existing: bool = True, crop_points_dir: Optional[str] = None,
+                          las_decode: str = "gpu") -> List[str]:
+    """LAS/NPY cloud -> every non-empty ``tile`` x ``tile`` crop as PNG + sidecar.  Returns the stems.
+
+    ``las_decode='gpu'`` (default): the point-data block of a ``.las`` file goes to the device as it
+    lies on disk and is decoded there (``lm_las_decode``, include/lm_las.h) -- the host never scales a
+    coordinate; ``'host'`` decodes with numpy first (what ``.npy`` inputs always do)."""
     import torch
     from .bev import BevRasterizer, crop_tiles
 
@@ -113,25 +121,44 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
     if channels[1] not in ELEVATION_CHANNELS:
         raise ValueError("channel index 1 must be an elevation channel (reference coor_img2pc.py:150)")
 
-    xyz, inten, read_off = load_cloud(las_filename)
-    if len(xyz) < MIN_POINTS:
-        print("too few lidar pts: ", len(xyz), las_filename)
-        return []
-    spec, local, params = plan_raster(xyz, read_off, pose, img_reso, ele_reso, tile, channels,
-                                      count16_dir is not None, las_filename)
-    pts = np.empty((len(local), 4), dtype=np.float32)
-    pts[:, :3] = local
-    pts[:, 3] = inten
-
     dev = torch.device(device)
+    if las_decode not in ("gpu", "host"):
+        raise ValueError("las_decode must be 'gpu' or 'host'")
+    if las_decode == "gpu" and os.path.splitext(las_filename)[1].lower() == ".las":
+        from .bev import decode_las, las_xform
+        raw, hdr = las_io.read_point_block(las_filename)
+        if hdr.n_points < MIN_POINTS:
+            print("too few lidar pts: ", hdr.n_points, las_filename)
+            return []
+        read_off = tuple(float(v) for v in hdr.offset)
+        params = PcImgParams(las_filename, read_off, tuple(pose), (0.0, 0.0), tuple(img_reso), 0.0, float(ele_reso))
+        with torch.cuda.device(dev):
+            pts_dev = decode_las(torch.from_numpy(raw).to(dev), hdr.n_points, las_xform(hdr, params))
+            ext = torch.stack([pts_dev[:, :3].amin(dim=0), pts_dev[:, :3].amax(dim=0)]).double().cpu().numpy()
+        spec = plan_from_extent(ext[0], ext[1], img_reso, ele_reso, tile, channels, count16_dir is not None)
+        pts = pts_dev.cpu().numpy() if crop_points_dir is not None else None
+        n_points = hdr.n_points
+    else:
+        xyz, inten, read_off = load_cloud(las_filename)
+        if len(xyz) < MIN_POINTS:
+            print("too few lidar pts: ", len(xyz), las_filename)
+            return []
+        spec, local, params = plan_raster(xyz, read_off, pose, img_reso, ele_reso, tile, channels,
+                                          count16_dir is not None, las_filename)
+        pts = np.empty((len(local), 4), dtype=np.float32)
+        pts[:, :3] = local
+        pts[:, 3] = inten
+        pts_dev = torch.from_numpy(pts).to(dev, non_blocking=True)
+        n_points = len(pts)
+
     key = (spec, dev)
     r = getattr(_tls, "raster", None)
-    if r is None or getattr(_tls, "key", None) != key or r.max_points < len(pts):
+    if r is None or getattr(_tls, "key", None) != key or r.max_points < n_points:
         outputs = ("image", "count16") if spec.count16 else ("image",)
-        r = BevRasterizer(spec, len(pts), device=dev, outputs=outputs)
+        r = BevRasterizer(spec, n_points, device=dev, outputs=outputs)
         _tls.raster, _tls.key = r, key
     with torch.cuda.device(dev):
-        out = r(torch.from_numpy(pts).to(dev, non_blocking=True))
+        out = r(pts_dev)
         crops = crop_tiles(out["image"], tile).cpu().numpy()
         crops16 = None
         if spec.count16:
@@ -171,7 +198,7 @@ def rasterize_single_file(las_filename: str, new_tiff_dir: str, new_param_dir: s
         stems.append(stem)
     with open(manifest, "w") as f:
         json.dump({"source": las_filename, "stems": stems, "grid": [spec.height, spec.width],
-                   "n_points": int(len(pts))}, f)
+                   "n_points": int(n_points)}, f)
     return stems
 
 

@@ -109,7 +109,7 @@ struct KParams {
 };
 
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
-    unsigned int pool_cursor;   // chunks handed out so far (chunk ids are cursor+1: id 0 = none)
+    unsigned int reserved0;
     unsigned int tile_counter;  // reduce_tiles scheduler
     unsigned int pad[6];
 };
@@ -121,11 +121,14 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t *tile_first;    // [T]
     uint32_t *tile_cursor;   // [T]
     uint32_t *tile_order;    // [T] tiles sorted heaviest first (reduce_tiles schedule)
+    uint32_t *cta_chunks;    // [bin CTAs] chunks each bin CTA used of its region
     uint2 *chunk_meta;       // [P] {tile, count}
     uint32_t *chunk_index;   // [P] per-tile chunk lists: id | (count-1) << 23
     uint32_t *pool;          // [P][CHUNK_RECS]
     uint32_t *acc;           // direct path: [6][H][W]
     uint32_t pool_chunks;    // P
+    uint32_t region;         // chunks per bin CTA: CTA b owns chunk ids [b * region, (b + 1) * region), local id 0 = none
+    uint32_t bin_grid;       // bin CTAs of this launch
 };
 
 struct Outs {
@@ -341,11 +344,14 @@ __device__ __forceinline__ void publish_chunk(const Ws &ws, uint32_t id, uint32_
 
 // Per-CTA append state, all in shared memory:
 //   pos[t]      how many records this CTA has appended to tile t so far (monotonic over the kernel)
-//   slot[t][4]  ring of chunk ids: record number q of tile t lives in chunk slot[t][(q / CHUNK) & 3]
+//   slot[t][2]  ring of 16-bit LOCAL chunk ids: record number q of tile t lives in chunk
+//               region_base + slot[t][(q / CHUNK) & 1]
 // A point's atomicAdd on pos[t] IS its reservation: it yields the chunk-block and the offset inside
-// it.  The thread that draws the first record of a block allocates that block's chunk (from a
-// per-CTA stash of ids refilled with one global atomic per STASH chunks).  Nothing in a batch is
-// serial: two balanced phases (reserve / store) separated by one barrier each.
+// it.  Every bin CTA owns a private region of the chunk pool (ids [b * region, (b + 1) * region)), so
+// the thread that draws the first record of a block allocates that block's chunk with one
+// shared-memory atomic -- no global allocator, no abandoned ids -- and 8 bytes of state per tile keep
+// four CTAs per SM up to ~2900 tiles.  Nothing in a batch is serial: two balanced phases
+// (reserve / store) separated by one barrier each.
 // A batch appends at most BIN_BATCH <= 2 * CHUNK records to a tile, i.e. it starts at most two new
 // blocks, so four ring slots can never wrap inside the window that is still being read.
 constexpr int CHUNK_LOG2 = LM_CHUNK_LOG2;
@@ -353,8 +359,7 @@ static_assert(BIN_PPT % 2 == 0, "z quotients are computed two points at a time")
 static_assert(BIN_BATCH <= 2 * CHUNK_RECS, "a batch may start at most two chunk blocks per tile");
 // a batch that fits one chunk starts at most ONE new block per tile: two ring slots are enough
 constexpr int NSLOT = BIN_BATCH <= CHUNK_RECS ? 2 : 4;
-constexpr int STASH = 128;            // chunk ids fetched per refill
-constexpr int STASH_LOW = 32;         // refill when fewer than this remain (the remainder is abandoned)
+constexpr uint32_t MAX_REGION = 65535;  // local chunk ids are 16-bit
 
 // A batched call (lm_bev_rasterize_batch) rasterises up to MAX_BATCH equally-shaped samples as ONE
 // stacked raster of n_samples * bH rows: sample s owns the 1024-point batches [first[s], first[s+1])
@@ -382,20 +387,20 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
     const uint32_t stage_bytes = LAS ? ((BIN_BATCH * rec_bytes + 15u) & ~15u) + 16u : BIN_BATCH * 16u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = kp.T;
-    // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u32
+    // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u16
     uint32_t sm_stage = smem_u32(smem_raw);
     uint32_t sm_pos = sm_stage + 2u * stage_bytes;
     uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
     // keep the three bases in registers: without this the compiler re-derives them (window base +
     // offsets, ~5 instructions) at every use because they are cheap to rematerialise
     asm volatile("" : "+r"(sm_stage), "+r"(sm_pos), "+r"(sm_slot));
-    __shared__ uint32_t s_stash[2][2];                                       // [which]{next id, end id}
-    __shared__ uint32_t s_active;                                            // which stash phase 1 draws from
+    __shared__ uint32_t s_next;                                              // next local chunk id of this CTA's region
     __shared__ __align__(8) uint64_t s_bar[2];                               // TMA completion barriers
 
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_active = 0; }
-    if (tid < 4) (&s_stash[0][0])[tid] = 0;
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_next = 1u; }
+    const uint32_t sm_next = smem_u32(&s_next);
+    const uint32_t region_base = blockIdx.x * ws.region;
     for (int t = tid; t < T; t += BIN_THREADS) sts_u32(sm_pos + 4u * t, 0u);
     __syncthreads();
 
@@ -444,12 +449,6 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
             geo = Geo{bt.off0[samp], bt.off1[samp], bt.zmin[samp], bt.row0[samp], bt.col0[samp], bt.bH};
             row_shift = samp * bt.bH;
         }
-        // stash refill (thread 0): the global atomic is in flight while everybody computes keys
-        const uint32_t act = s_active;
-        uint32_t refill = 0;
-        const bool do_refill = tid == 0 && (int)(s_stash[act][1] - s_stash[act][0]) < STASH_LOW;
-        if (do_refill) refill = atomicAdd(&ws.ctl->pool_cursor, (uint32_t)STASH) + 1u;
-
         mbar_wait(&s_bar[buf], ((uint32_t)k >> 1) & 1u);     // this batch's records have landed
         float4 p[BIN_PPT];
         const uint32_t my_stage = sm_stage + buf * stage_bytes + (uint32_t)tid * rec_bytes;
@@ -519,43 +518,32 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
                 ps[j] = atoms_add(sm_pos + 4u * tl[j], 1u);
-                sa[j] = sm_slot + (4u * NSLOT) * tl[j] + ((ps[j] >> (CHUNK_LOG2 - 2)) & (4u * (NSLOT - 1)));   // ring slot of its block
+                sa[j] = sm_slot + (2u * NSLOT) * tl[j] + ((ps[j] >> (CHUNK_LOG2 - 1)) & (2u * (NSLOT - 1)));   // ring slot of its block
                 if ((ps[j] & (CHUNK_RECS - 1)) == 0) {
-                    uint32_t id = atomicAdd(&s_stash[act][0], 1u);
-                    if (id >= s_stash[act][1]) id = atomicAdd(&ws.ctl->pool_cursor, 1u) + 1u;     // stash dry: go global
-                    if (id >= ws.pool_chunks) {                  // cannot happen with lm_bev_workspace_bytes' size
+                    uint32_t id = atoms_add(sm_next, 1u);
+                    if (id >= ws.region) {                       // cannot happen with lm_bev_workspace_bytes' size
                         atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
-                        id = 0;                                  // chunk 0 is a scratch chunk nobody reads
+                        id = 0;                                  // local chunk 0 is a scratch chunk nobody reads
                     }
-                    sts_u32(sa[j], id);
+                    sts_u16(sa[j], id);
                 }
             }
         }
         __syncthreads();
-        // install the refilled stash for the next reserve phase (nobody allocates in phase 2)
-        if (do_refill) {
-            if (refill + STASH <= ws.pool_chunks) {
-                s_stash[act ^ 1][0] = refill;
-                s_stash[act ^ 1][1] = refill + STASH;
-                s_active = act ^ 1;
-            } else {
-                atomicOr(&ws.stats->error, (uint32_t)LM_DEV_ERR_POOL);
-            }
-        }
         // ---- phase 2: store.  Lanes that hit the same tile drew consecutive positions, so they write
         //      neighbouring words; L2 merges partial sectors before they reach HBM.
         uint32_t cid[BIN_PPT];
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j)
-            cid[j] = tl[j] != INVALID_U32 ? lds_u32(sa[j]) : 0u;
+            cid[j] = tl[j] != INVALID_U32 ? region_base + lds_u16(sa[j]) : 0u;
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
                 const uint32_t off = ps[j] & (CHUNK_RECS - 1);
                 ws.pool[cid[j] * (uint32_t)CHUNK_RECS + off] = rec[j];        // record index < 2^32 (checked on the host)
                 if (off == 0 && ps[j] != 0) {                    // the previous block of this tile is complete
-                    const uint32_t prev = lds_u32(sm_slot + 4u * (tl[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
-                    if (prev) publish_chunk(ws, prev, CHUNK_RECS, tl[j]);
+                    const uint32_t prev = lds_u16(sm_slot + 2u * (tl[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
+                    if (prev) publish_chunk(ws, region_base + prev, CHUNK_RECS, tl[j]);
                 }
             }
         }
@@ -568,12 +556,17 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         if (q) {
             my_valid += q;
             const uint32_t last = q - 1;
-            const uint32_t id = lds_u32(sm_slot + 4u * (t * NSLOT + ((last >> CHUNK_LOG2) & (NSLOT - 1))));
-            if (id) publish_chunk(ws, id, (last & (CHUNK_RECS - 1)) + 1u, (uint32_t)t);
+            const uint32_t id = lds_u16(sm_slot + 2u * (t * NSLOT + ((last >> CHUNK_LOG2) & (NSLOT - 1))));
+            if (id) publish_chunk(ws, region_base + id, (last & (CHUNK_RECS - 1)) + 1u, (uint32_t)t);
         }
     }
     for (int o = 16; o; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
     if ((tid & 31) == 0 && my_valid) atomicAdd((unsigned long long *)&ws.stats->n_valid, (unsigned long long)my_valid);
+    if (tid == 0) {                                              // nobody allocates after the last batch's first barrier
+        const uint32_t used = min(s_next, ws.region) - 1u;
+        ws.cta_chunks[blockIdx.x] = used;
+        if (used) atomicAdd(&ws.stats->n_chunks, used);
+    }
 }
 
 
@@ -656,8 +649,6 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         s_err = ws.stats->error & LM_DEV_ERR_POOL;
-        const uint32_t used = ws.ctl->pool_cursor;
-        ws.stats->n_chunks = used < ws.pool_chunks ? used : ws.pool_chunks;
         ws.stats->n_tiles = (uint32_t)T;
     }
     s_lvl[tid] = 0;
@@ -699,16 +690,17 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
 
 __global__ void index_chunks_kernel(Ws ws) {
     if (ws.stats->error & LM_DEV_ERR_POOL) return;
-    const uint32_t used = ws.ctl->pool_cursor;    // ids 1..used
-    const uint32_t last = used < ws.pool_chunks - 1u ? used : ws.pool_chunks - 1u;
-    for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= last; id += gridDim.x * blockDim.x) {
-        const uint2 m = ws.chunk_meta[id];
-        if (m.y == 0) continue;                      // abandoned stash id
+    // chunk ids are (bin CTA, local id) pairs: CTA b used local ids 1 .. cta_chunks[b] of its region
+    const uint32_t total = ws.bin_grid * ws.region;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
+        const uint32_t b = id / ws.region, k = id - b * ws.region;
+        if (k == 0 || k > ws.cta_chunks[b]) continue;
+        const uint2 m = ws.chunk_meta[id];           // every allocated chunk was published with count >= 1
         const uint32_t np = (m.y + PIECE_RECS - 1) / PIECE_RECS;               // non-empty pieces of this chunk
         const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], np);
-        for (uint32_t k = 0; k < np; ++k) {
-            const uint32_t c = min(m.y - k * PIECE_RECS, (uint32_t)PIECE_RECS);
-            ws.chunk_index[slot + k] = (id * HALVES + k) | ((c - 1u) << IDX_ID_BITS);
+        for (uint32_t q = 0; q < np; ++q) {
+            const uint32_t c = min(m.y - q * PIECE_RECS, (uint32_t)PIECE_RECS);
+            ws.chunk_index[slot + q] = (id * HALVES + q) | ((c - 1u) << IDX_ID_BITS);
         }
     }
 }
@@ -1161,7 +1153,15 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     return k;
 }
 
-size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * 4 * (1 + NSLOT); }
+size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * (4 + 2 * NSLOT); }
+
+// chunks per bin CTA when `grid` CTAs share `nb` batches: the chunks its points can fill, one open
+// chunk per tile, and the unused local id 0
+constexpr long long CHUNKS_PER_BATCH = (BIN_BATCH + CHUNK_RECS - 1) / CHUNK_RECS;
+long long bin_region(long long nb, long long grid, int T) {
+    const long long per = (nb + grid - 1) / grid;
+    return per * CHUNKS_PER_BATCH + T + 1;
+}
 
 // upper bound of the bin_points grid for T tiles (shared memory limits the CTAs per SM); the record
 // pool reserves one open chunk per (CTA, tile), so the workspace size and the launch both use it
@@ -1191,7 +1191,7 @@ int window_rows(const lm_bev_params *p, int tile_h_log2) {
 }
 
 struct Layout {
-    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, zero_bytes;
+    size_t off_ctl, off_nchunks, off_first, off_cursor, off_order, off_cta, zero_bytes;
     size_t off_meta, off_index, off_pool, off_acc, total;
     uint32_t pool_chunks;
     int bin_ctas;
@@ -1202,7 +1202,7 @@ int bin_ctas_for(long long n) {
     return (int)(nb < 1 ? 1 : (nb < MAX_BIN_CTAS ? nb : MAX_BIN_CTAS));
 }
 
-// Binned workspace: [stats | ctl | tile tables | per-CTA open-chunk state] (zeroed per call)
+// Binned workspace: [stats | ctl | tile tables | chunks used per bin CTA] (zeroed per call)
 //                   [chunk side table | chunk index | record pool]
 int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L) {
     memset(L, 0, sizeof(*L));
@@ -1221,19 +1221,44 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
     L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
-    // full chunks + one open chunk per (CTA, tile) + chunk ids a CTA may abandon in its stash
-    const unsigned long long full = (unsigned long long)((n + CHUNK_RECS - 1) / CHUNK_RECS);
-    const unsigned long long chunks = full + full / (STASH / STASH_LOW) +
-                                      (unsigned long long)bin_ctas_bound(T) * ((unsigned long long)T + 2 * STASH) + 2ull;
+    const long long gb = bin_ctas_bound(T);
+    L->off_cta = o;     o = align_up(o + (size_t)gb * 4, 256);
+    L->zero_bytes = o;
+    // every bin CTA owns a region of the pool (bin_region): whatever grid <= gb the launch ends up with,
+    // grid * region <= batches + gb * (T + 2).  A batched call adds one partial batch per sample.
+    const unsigned long long nbb = (unsigned long long)(n / BIN_BATCH) + 1ull + MAX_BATCH;
+    const unsigned long long chunks = nbb * CHUNKS_PER_BATCH + (unsigned long long)gb * ((unsigned long long)T + 2ull) + 1ull;
     if (chunks * HALVES >= (1ull << IDX_ID_BITS))     // piece ids share a word with the count; record indices are 32-bit
         return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^23 chunks: shard the call (fewer points or a smaller row window)");
     L->pool_chunks = (uint32_t)chunks;
-    // the side table is zeroed too: count == 0 marks chunk ids that were handed out but never used
     L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
-    L->zero_bytes = o;
     L->off_index = o; o = align_up(o + (size_t)chunks * HALVES * 4, 256);
     L->off_pool = o;  o = align_up(o + (size_t)chunks * CHUNK_RECS * 4, 256);
     L->total = o;
+    return LM_OK;
+}
+
+// Grid and chunk region of one bin launch (the same values in every stage-split call of a raster):
+// persistent, one wave of resident CTAs, each owning a contiguous range of the nb batches.
+int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int sms, const Layout &L, Ws *ws, int *grid_out) {
+    if (smem > 220 * 1024) return fail(LM_ERR_UNSUPPORTED, "%zu bytes of shared memory per bin CTA: too many tiles / too long records", smem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BIN_THREADS, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
+    long long grid = (long long)sms * (occ < 1 ? 1 : occ);
+    if (grid > bin_ctas_bound(T)) grid = bin_ctas_bound(T);
+    if (grid > nb) grid = nb;
+    if (grid < 1) grid = 1;
+    const long long region = bin_region(nb, grid, T);
+    if (region > (long long)MAX_REGION)
+        return fail(LM_ERR_UNSUPPORTED, "%lld chunks per bin CTA exceed the 16-bit local chunk ids: shard the call", region);
+    if ((unsigned long long)grid * (unsigned long long)region > L.pool_chunks)
+        return fail(LM_ERR_WORKSPACE, "record pool of %u chunks < %lld x %lld", L.pool_chunks, grid, region);
+    ws->region = (uint32_t)region;
+    ws->bin_grid = (uint32_t)grid;
+    *grid_out = (int)grid;
     return LM_OK;
 }
 
@@ -1390,6 +1415,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
     ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
     ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
     ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
+    ws.cta_chunks = reinterpret_cast<uint32_t *>(w + L.off_cta);
     ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
     ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
     ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
@@ -1406,40 +1432,25 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
         kp.orow = win * wrows;
         kp.band = banded ? out->acc_band : 0;
         cudaError_t e = cudaSuccess;
+        const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
+        const size_t smem = las ? 2 * (size_t)las_stage_bytes((uint32_t)las->record_length, BIN_BATCH) + (size_t)kp.T * (4 + 2 * NSLOT)
+                                : bin_smem_bytes(kp.T);
+        int grid = 0;
+        ws.region = 1;
+        ws.bin_grid = 0;
+        if (n_points > 0) {
+            rc = bin_geometry(las ? (const void *)bin_points_las_kernel : (const void *)bin_points_kernel, smem, nb, kp.T, sms, L, &ws, &grid);
+            if (rc) return rc;
+        }
         if (stages & LM_STAGE_BIN) {
             // stats (first 64 bytes) accumulate over the windows; everything else restarts
             const size_t skip = win == 0 && !keep_stats ? 0 : L.off_ctl;
             e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
             if (e != cudaSuccess) return cuda_fail(e, "memset");
-            if (n_points > 0 && las) {
-                const size_t smem = 2 * (size_t)las_stage_bytes((uint32_t)las->record_length, BIN_BATCH) + (size_t)kp.T * 4 * (1 + NSLOT);
-                if (smem > 220 * 1024)
-                    return fail(LM_ERR_UNSUPPORTED, "%d-byte records x %d tiles do not fit in shared memory: use lm_las_decode first",
-                                las->record_length, kp.T);
-                e = cudaFuncSetAttribute(bin_points_las_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return cuda_fail(e, "bin_points_las smem attribute");
-                int occ = 1;
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_las_kernel, BIN_THREADS, smem);
-                if (e != cudaSuccess) return cuda_fail(e, "bin_points_las occupancy");
-                long long grid = (long long)sms * (occ < 1 ? 1 : occ);
-                if (grid > bin_ctas_bound(kp.T)) grid = bin_ctas_bound(kp.T);
-                const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
-                if (grid > nb) grid = nb;
-                bin_points_las_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, *las, reinterpret_cast<const unsigned char *>(points_dev), n_points, ws);
-            } else if (n_points > 0) {
-                const size_t smem = bin_smem_bytes(kp.T);
-                e = cudaFuncSetAttribute(bin_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-                // persistent: one wave of resident CTAs, each owning a contiguous range of batches
-                int occ = 1;
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_kernel, BIN_THREADS, smem);
-                if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
-                long long grid = (long long)sms * (occ < 1 ? 1 : occ);
-                if (grid > bin_ctas_bound(kp.T)) grid = bin_ctas_bound(kp.T);
-                const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
-                if (grid > nb) grid = nb;
-                bin_points_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
-            }
+            if (n_points > 0 && las)
+                bin_points_las_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, *las, reinterpret_cast<const unsigned char *>(points_dev), n_points, ws);
+            else if (n_points > 0)
+                bin_points_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
         }
         if (stages & LM_STAGE_INDEX) {
             scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
@@ -1634,6 +1645,7 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
         ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
         ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
         ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
+        ws.cta_chunks = reinterpret_cast<uint32_t *>(w + L.off_cta);
         ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
         ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
         ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
@@ -1642,17 +1654,14 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
         const size_t skip = s0 == 0 ? 0 : L.off_ctl;             // stats accumulate over the launch sets
         cudaError_t e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
         if (e != cudaSuccess) return cuda_fail(e, "memset");
+        ws.region = 1;
+        ws.bin_grid = 0;
         if (batches > 0) {
             const size_t smem = bin_smem_bytes(kp.T);
-            e = cudaFuncSetAttribute(bin_points_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-            int occ = 1;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bin_points_batch_kernel, BIN_THREADS, smem);
-            if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
-            long long grid = (long long)sms * (occ < 1 ? 1 : occ);
-            if (grid > bin_ctas_bound(kp.T)) grid = bin_ctas_bound(kp.T);
-            if (grid > (long long)batches) grid = batches;
-            bin_points_batch_kernel<<<(int)grid, BIN_THREADS, smem, st>>>(kp, bt, ws);
+            int grid = 0;
+            rc = bin_geometry((const void *)bin_points_batch_kernel, smem, (long long)batches, kp.T, sms, L, &ws, &grid);
+            if (rc) return rc;
+            bin_points_batch_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, bt, ws);
         }
         scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
         if (batches > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);

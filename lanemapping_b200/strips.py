@@ -172,8 +172,8 @@ class StripRasterizer:
 
     # -- pipelined steps: rasterise scene k while scene k-1's mosaic is still being gathered -----------
     def step(self, points: torch.Tensor) -> int:
-        """Enqueue one full scene (rasterise + halo merge on the current stream, mosaic all-gather on a
-        side stream) and return its buffer slot; ``mosaic(slot)`` waits for and returns the result.
+        """Enqueue one full scene (rasterisation on the current stream; halo exchange + merge and the
+        mosaic all-gather on a side stream) and return its buffer slot; ``mosaic(slot)`` waits for and returns the result.
         At most two scenes are in flight: slot k % 2 is reused by scene k + 2."""
         if self.device.type != "cuda":
             raise RuntimeError("step() needs CUDA streams; use rasterize() + gather() on CPU back ends")
@@ -188,14 +188,16 @@ class StripRasterizer:
             main.wait_event(self._gather_done[k])          # the strip buffer is free once its gather has run
         p = self.plan
         out = self.raster(points, out=self._outs[k])
-        if self.need_acc:
-            self._exchange_and_merge(out)
         hl = self.local_spec.height
         strip = out["image"][p.top:hl - p.bottom]
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(self._comm_stream):
+            # everything after the local rasterisation -- halo exchange, merge, re-finish of the edge
+            # bands, mosaic gather -- runs on the side stream, under the next scene's rasterisation
             self._comm_stream.wait_event(ready)
+            if self.need_acc:
+                self._exchange_and_merge(out)
             self._mosaics[k] = self.gather(strip)
             done = torch.cuda.Event()
             done.record(self._comm_stream)

@@ -15,6 +15,7 @@ contracts its in-tree code does fix):
   inverse_io2.json                    a harder inverse case: vertices inside / on the rim of empty holes
                                       (in-place hole filling that later vertices see), a non-unit quaternion
   inverse_io3.npz                     random crops / polylines / poses through the same reference function
+  labels_seq.json                     the sequence JSON the same call writes (save_seq)
   labels_in.json, labels_*.png        reference data/convert_data.write_instance_orientation_seq run on
                                       synthetic polylines: the four label rasters it writes
 """
@@ -98,6 +99,8 @@ def make_labels(ref_convert):
     with tempfile.TemporaryDirectory() as d:
         names = [os.path.join(d, k) for k in ("seq.json", "sem.png", "ins.png", "ori.png", "endp.png")]
         ref_convert.write_instance_orientation_seq(seqs.copy(), lens, semantic, instance, orient, *names)   # :319-369
+        import shutil
+        shutil.copy(names[0], os.path.join(HERE, "labels_seq.json"))                 # the reference's save_seq output
         for k, src in zip(("semantic", "instance", "orient", "endp"), names[1:]):
             img = cv2.imread(src, cv2.IMREAD_UNCHANGED)
             assert img.dtype == np.uint8 and img.shape == (1152, 1152), (img.dtype, img.shape)

@@ -81,6 +81,12 @@ def test_offline_converter_writes_reference_compatible_files(bev, tmp_path):
     stems = multiprocessing_las_files([las_path], tiff, param, num_process=2, crop_points_dir=cpts)
     assert stems == ["181013_0001", "181013_0002"] and all(len(s) == 11 for s in stems)   # 60 m -> 2 crops of 57.6 m
     assert multiprocessing_las_files([las_path], tiff, param, num_process=1) == stems       # resumable: manifest hit
+    # the default decodes the LAS records on the GPU; the host (numpy) decode gives the same files
+    tiff_h, param_h = str(tmp_path / "tiff_host"), str(tmp_path / "param_host")
+    assert multiprocessing_las_files([las_path], tiff_h, param_h, num_process=1, las_decode="host") == stems
+    for s_ in stems:
+        assert open(os.path.join(tiff, s_ + ".png"), "rb").read() == open(os.path.join(tiff_h, s_ + ".png"), "rb").read()
+        assert open(os.path.join(param, s_ + ".txt")).read() == open(os.path.join(param_h, s_ + ".txt")).read()
     xyz, inten_rd, hdr = las.read_las(las_path)
     for k, stem in enumerate(stems):
         img = np.array(Image.open(os.path.join(tiff, stem + ".png")), dtype=np.uint8)        # loader :87-88

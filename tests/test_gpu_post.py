@@ -160,3 +160,24 @@ def test_color_jitter_matches_torchvision(post):
     for k in range(2):
         fn_idx, b, c, s, _ = cj.get_params(cj.brightness, cj.contrast, cj.saturation, cj.hue)
         assert mine[k] == (fn_idx.tolist(), b, c, s)
+
+
+# ---- the reference-signature entry points (lanemapping_b200/ref_api.py) ----------------------
+def test_ref_api_write_instance_orientation_seq_writes_the_reference_files(post, tmp_path):
+    import cv2
+    from lanemapping_b200 import ref_api
+    d = json.load(open(os.path.join(G, "labels_in.json")))
+    names = [str(tmp_path / k) for k in ("seq.json", "sem.png", "ins.png", "ori.png", "endp.png")]
+    ref_api.write_instance_orientation_seq(np.array(d["seqs"]), d["lens"], d["semantic"], d["instance"],
+                                           np.array(d["orient"]), *names)
+    for k, path in zip(("semantic", "instance", "orient", "endp"), names[1:]):
+        assert np.array_equal(cv2.imread(path, cv2.IMREAD_UNCHANGED), np.array(Image.open(os.path.join(G, f"labels_{k}.png"))))
+    assert json.load(open(names[0])) == json.load(open(os.path.join(G, "labels_seq.json")))
+
+
+def test_ref_api_transform_coordinate_from_img_2_pc(post):
+    from lanemapping_b200 import ref_api
+    d = json.load(open(os.path.join(G, "inverse_io2.json")))
+    world = ref_api.transform_coordinate_from_img_2_pc(d["params"], np.array(d["img_seqs"]), d["img_seq_lens"],
+                                                       Image.open(os.path.join(G, "golden_crop.png")))
+    assert np.array_equal(world, np.array(d["world"]))

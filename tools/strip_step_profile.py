@@ -21,3 +21,25 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); r(cloud, out=out); e1.record(); e1.synchronize()
 print("strip raster step ms:", e0.elapsed_time(e1), r.stats())
+from lanemapping_b200 import _cabi
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+best = [1e9] * 3
+for _ in range(5):
+    for k, stg in enumerate((_cabi.STAGE_BIN, _cabi.STAGE_INDEX, _cabi.STAGE_REDUCE)):
+        ev[k].record(); r(cloud, out=out, stages=stg)
+    ev[3].record(); ev[3].synchronize()
+    best = [min(b, ev[k].elapsed_time(ev[k + 1])) for k, b in enumerate(best)]
+print(f"strip stages: bin {best[0]:.3f}  scan+index {best[1]:.3f}  reduce {best[2]:.3f} ms")
+# the same points without halo bands / raw accumulators (what an N = 1 run of this geometry would do)
+plain = spec.window(r0, r1)
+r2 = BevRasterizer(plain, n, outputs=("image",))
+o2 = r2.alloc_outputs()
+for _ in range(2):
+    r2(cloud, out=o2)
+best = [1e9] * 3
+for _ in range(5):
+    for k, stg in enumerate((_cabi.STAGE_BIN, _cabi.STAGE_INDEX, _cabi.STAGE_REDUCE)):
+        ev[k].record(); r2(cloud, out=o2, stages=stg)
+    ev[3].record(); ev[3].synchronize()
+    best = [min(b, ev[k].elapsed_time(ev[k + 1])) for k, b in enumerate(best)]
+print(f"no-halo stages: bin {best[0]:.3f}  scan+index {best[1]:.3f}  reduce {best[2]:.3f} ms  {r2.stats()}")
