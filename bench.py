@@ -70,11 +70,8 @@ def cpu_rasterize_timed(cloud, spec, processes, reps):
     index range each strip needs (scan-ordered clouds: contiguous ranges with a 2 m margin)."""
     from oracle import bev_oracle as O
     n = len(cloud)
-    H = spec.height
     P = max(1, processes)
-    edges = [H * k // P for k in range(P + 1)]
-    margin = int(2.5 / (H * spec.img_reso[0]) * n) + 1
-    ranges = [(max(0, int(edges[k] / H * n) - margin), min(n, int(edges[k + 1] / H * n) + margin)) for k in range(P)]
+    ranges = O.scan_point_ranges(n, spec, P)
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()

@@ -106,6 +106,7 @@ struct KParams {
     int oH, orow;   // height of the output buffers and this window's first row inside them
                     // (a raster with more tiles than one launch handles is done as row windows)
     int bH;         // > 0: batched call, the raster is a stack of samples of bH rows each (proj is [B][C][bH][W])
+    int stream_hint;   // bin_points: bit 0 = the point stream is loaded with an L2 evict-first policy, bit 1 = records are stored evict-last
 };
 
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
@@ -430,7 +431,8 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
     if (tid == 0 && my_batches > 0) {
         uint32_t np;
         const void *src = batch_src(0, samp_pf, np);
-        bulk_load(smem_raw, src, batch_bytes(np), &s_bar[0]);
+        if (kp.stream_hint & 1) bulk_load_stream(smem_raw, src, batch_bytes(np), &s_bar[0]);
+        else bulk_load(smem_raw, src, batch_bytes(np), &s_bar[0]);
     }
     Geo geo = geo_of(kp);
     int row_shift = 0;                                                       // first row of the sample in the stacked raster
@@ -441,7 +443,8 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         if (tid == 0 && k + 1 < my_batches) {
             uint32_t np;
             const void *src = batch_src(k + 1, samp_pf, np);
-            bulk_load(smem_raw + (buf ^ 1u) * stage_bytes, src, batch_bytes(np), &s_bar[buf ^ 1u]);
+            if (kp.stream_hint & 1) bulk_load_stream(smem_raw + (buf ^ 1u) * stage_bytes, src, batch_bytes(np), &s_bar[buf ^ 1u]);
+            else bulk_load(smem_raw + (buf ^ 1u) * stage_bytes, src, batch_bytes(np), &s_bar[buf ^ 1u]);
         }
         uint32_t npts;
         batch_src(k, samp, npts);
@@ -540,7 +543,9 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
                 const uint32_t off = ps[j] & (CHUNK_RECS - 1);
-                ws.pool[cid[j] * (uint32_t)CHUNK_RECS + off] = rec[j];        // record index < 2^32 (checked on the host)
+                uint32_t *dst = ws.pool + (cid[j] * (uint32_t)CHUNK_RECS + off);   // record index < 2^32 (checked on the host)
+                if (kp.stream_hint & 2) stg_u32_hint(dst, rec[j], l2_policy_evict_last());
+                else *dst = rec[j];
                 if (off == 0 && ps[j] != 0) {                    // the previous block of this tile is complete
                     const uint32_t prev = lds_u16(sm_slot + 2u * (tl[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
                     if (prev) publish_chunk(ws, region_base + prev, CHUNK_RECS, tl[j]);
@@ -1121,6 +1126,12 @@ int validate(const lm_bev_params *p) {
     return LM_OK;
 }
 
+// L2 policy of the point stream in bin_points (LM_BEV_STREAM_HINT=0/1 overrides; measured in profiles/)
+int stream_hint_default() {
+    if (const char *e = getenv("LM_BEV_STREAM_HINT")) return atoi(e) & 3;
+    return 0;
+}
+
 KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     KParams k;
     k.H = p->height; k.W = p->width; k.row0 = p->row0; k.col0 = p->col0;
@@ -1150,6 +1161,7 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     k.orow = 0;
     k.band = 0;
     k.bH = 0;
+    k.stream_hint = stream_hint_default();
     return k;
 }
 
@@ -1247,6 +1259,10 @@ int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int sms, 
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BIN_THREADS, smem);
     if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
+    if (const char *ev = getenv("LM_BEV_BIN_CTAS_PER_SM")) {      // tuning knob: fewer, faster-moving bin CTAs
+        const int v = atoi(ev);
+        if (v >= 1 && v < occ) occ = v;
+    }
     long long grid = (long long)sms * (occ < 1 ? 1 : occ);
     if (grid > bin_ctas_bound(T)) grid = bin_ctas_bound(T);
     if (grid > nb) grid = nb;

@@ -171,6 +171,17 @@ def _pool_strip(args):
     return r0, r1, rasterize(_POOL_PTS[lo:hi], sub)
 
 
+def scan_point_ranges(n, spec, processes, margin_m=2.5):
+    """Point index ranges per row strip for a single-road scan-ordered cloud (synth.make_cloud,
+    order='scan': along-track position grows linearly with the index, +-1 m jitter): the strip's
+    own share of the indices widened by ``margin_m`` metres of track on both sides."""
+    H = spec.height
+    P = max(1, int(processes))
+    edges = [H * k // P for k in range(P + 1)]
+    margin = int(margin_m / (H * spec.img_reso[0]) * n) + 1
+    return [(max(0, int(edges[k] / H * n) - margin), min(n, int(edges[k + 1] / H * n) + margin)) for k in range(P)]
+
+
 def rasterize_pool(pts, spec, processes, point_ranges=None):
     """Row-strip parallel rasterise with ``processes`` forked workers.
 
