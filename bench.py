@@ -8,8 +8,9 @@ A *step* is one pass of the hot path over one synthetic cloud.
   N = 1   BASELINE.json configs[1]: 100 M-point road segment -> 11520 x 1152 x 3 u8 at 0.05 m.
   N > 1   configs[2] geometry, weak scaling: every rank owns one 1440-row strip of an
           (1440 N) x 11520 scene with 1.25e8 points (N = 8 is exactly the 1 B-point scene);
-          the step includes the NCCL halo merge and the mosaic all-gather (the gather of scene k runs
-          on a side stream under the rasterisation of scene k+1; all gathers finish inside the timed region).
+          the step includes the NCCL halo merge and the mosaic gather on rank 0 (--gather all: all-gather
+          on every rank); the exchange and the gather of scene k run on a side stream under the
+          rasterisation of scene k+1 and all of them finish inside the timed region.
 ``value``  device-resident throughput (inputs in HBM when the clock starts), CUDA events,
            max over ranks.   ``e2e``: the same metric through the host-buffer API
            (pinned H2D of the points + D2H of the finished raster inside the timed region).
@@ -31,6 +32,9 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+# strip boundaries on multiples of 32 rows: the 1440-row strips of the weak-scaling scene come out equal,
+# so the mosaic gather is one all_gather_into_tensor straight from the strips (no padding, no concatenation)
+STRIP_ALIGN = 32
 METRIC = "bev_raster_mpoints_per_s"
 UNIT = "Mpoints/s"
 
@@ -58,7 +62,7 @@ def workload(n_gpus: int, rank: int, points_override: int = 0):
         sp = BevSpec(1440 * n_gpus, 11520, channels=ch)
         n = points_override or 125_000_000
         name = (f"configs[2] geometry, weak scaling: {n_gpus} strips of 1440x11520 cells @0.05 m, "
-                f"{n / 1e6:.0f}M points per GPU, halo merge + mosaic all-gather in the step")
+                f"{n / 1e6:.0f}M points per GPU, halo merge + mosaic gather in the step")
     return replace(sp, local_min_ele=default_min_ele(BevSpec(1152, 1152))), n, name
 
 
@@ -201,7 +205,7 @@ def run_ours(args):
     if args.gpus == 1:
         cloud = make_cloud(n_pts, spec, order=args.order)
     else:
-        r0, r1 = strip_bounds(spec.height, world, 128)[rank]
+        r0, r1 = strip_bounds(spec.height, world, STRIP_ALIGN)[rank]
         # the strip's own points; the +-1 m scan jitter strays up to 20 rows into the neighbours' strips
         cloud = make_cloud(n_pts, spec.window(r0, r1), order=args.order, seed=2021 + rank)
 
@@ -215,6 +219,15 @@ def run_ours(args):
         cpu_baseline = {"value": round(n_sample / dt / 1e6, 3), "unit": UNIT, "cores": P, "kind": "port",
                         "sample": f"{n_sample} points = first {sub.height} rows of the workload at full density, "
                                   f"numpy oracle over multiprocessing.Pool({P}) row strips, best of 2"}
+        try:      # for scale: the plain-C restatement of the same spec, one scalar loop on one core
+            from oracle import c_oracle as CO
+            m = min(len(sample_cloud), 10_000_000)
+            CO.rasterize(sample_cloud[:1000], sub)
+            t0 = time.perf_counter()
+            CO.accumulate(sample_cloud[:m], sub)
+            cpu_baseline["c_port_1core"] = round(m / (time.perf_counter() - t0) / 1e6, 3)
+        except Exception:
+            pass
         del sample_cloud
 
     import torch
@@ -258,7 +271,8 @@ def run_ours(args):
         launches_per_step = 4      # bin_points, scan_tiles, index_chunks, reduce_tiles (+1 memset node)
     else:
         from lanemapping_b200.strips import StripRasterizer
-        sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev)
+        sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev, align=STRIP_ALIGN,
+                             gather_root=0 if args.gather == "root" else None)
         mosaic_holder = {}
 
         def step():
@@ -305,8 +319,8 @@ def run_ours(args):
         def e2e_step():
             dev_in.copy_(host_pts, non_blocking=True)
             slot = sr.step(dev_in)
-            mosaic = sr.mosaic(slot)
-            host_strip.copy_(mosaic[r0:r1], non_blocking=True)
+            sr.mosaic(slot)                                   # the scene's merge + gather are part of the step
+            host_strip.copy_(sr.strip_of(slot), non_blocking=True)
             stream.synchronize()
         d2h = host_strip.numel()
     Ke = max(1, min(K, args.e2e_steps))
@@ -336,6 +350,7 @@ def run_ours(args):
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": name, "order": args.order, "algo": args.algo,
+                       **({"mosaic": "gathered on rank 0" if args.gather == "root" else "all-gathered on every rank"} if args.gpus > 1 else {}),
                        "points_per_gpu": n_pts, "valid_points_rank0": int(n_valid),
                        "l2_policy": "inputs (1.6+ GB of points per step) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the launch stream, barrier+synchronize both sides, max over ranks"},
@@ -387,6 +402,8 @@ def main():
     ap.add_argument("--algo", default="binned", choices=["binned", "direct"])
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (debug)")
     ap.add_argument("--halo", type=int, default=64)
+    ap.add_argument("--gather", default="root", choices=["root", "all"],
+                    help="N > 1: assemble the mosaic on rank 0 (gather) or on every rank (all-gather)")
     ap.add_argument("--cpu-points", type=int, default=20_000_000, help="bounded sample for the CPU arm")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")

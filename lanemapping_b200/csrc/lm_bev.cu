@@ -106,7 +106,7 @@ struct KParams {
     int oH, orow;   // height of the output buffers and this window's first row inside them
                     // (a raster with more tiles than one launch handles is done as row windows)
     int bH;         // > 0: batched call, the raster is a stack of samples of bH rows each (proj is [B][C][bH][W])
-    int stream_hint;   // bin_points: bit 0 = the point stream is loaded with an L2 evict-first policy, bit 1 = records are stored evict-last
+    int stream_hint;   // bin_points: 1 = the point stream is loaded with an L2 evict-first policy (off: profiles/r01_v11_hint_sweep.txt)
 };
 
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
@@ -543,9 +543,7 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
                 const uint32_t off = ps[j] & (CHUNK_RECS - 1);
-                uint32_t *dst = ws.pool + (cid[j] * (uint32_t)CHUNK_RECS + off);   // record index < 2^32 (checked on the host)
-                if (kp.stream_hint & 2) stg_u32_hint(dst, rec[j], l2_policy_evict_last());
-                else *dst = rec[j];
+                ws.pool[cid[j] * (uint32_t)CHUNK_RECS + off] = rec[j];        // record index < 2^32 (checked on the host)
                 if (off == 0 && ps[j] != 0) {                    // the previous block of this tile is complete
                     const uint32_t prev = lds_u16(sm_slot + 2u * (tl[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
                     if (prev) publish_chunk(ws, region_base + prev, CHUNK_RECS, tl[j]);
@@ -1128,7 +1126,7 @@ int validate(const lm_bev_params *p) {
 
 // L2 policy of the point stream in bin_points (LM_BEV_STREAM_HINT=0/1 overrides; measured in profiles/)
 int stream_hint_default() {
-    if (const char *e = getenv("LM_BEV_STREAM_HINT")) return atoi(e) & 3;
+    if (const char *e = getenv("LM_BEV_STREAM_HINT")) return atoi(e) & 1;
     return 0;
 }
 
@@ -1252,16 +1250,22 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
 
 // Grid and chunk region of one bin launch (the same values in every stage-split call of a raster):
 // persistent, one wave of resident CTAs, each owning a contiguous range of the nb batches.
-int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int sms, const Layout &L, Ws *ws, int *grid_out) {
+int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles_x, int sms, const Layout &L, Ws *ws, int *grid_out) {
     if (smem > 220 * 1024) return fail(LM_ERR_UNSUPPORTED, "%zu bytes of shared memory per bin CTA: too many tiles / too long records", smem);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BIN_THREADS, smem);
     if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
-    if (const char *ev = getenv("LM_BEV_BIN_CTAS_PER_SM")) {      // tuning knob: fewer, faster-moving bin CTAs
+    // A raster wider than four crops is a multi-road scene: the scan visits one road at a time and its
+    // stray returns spread over every tile column, so every (CTA, tile) pair keeps a slowly filling open
+    // chunk.  Fewer, faster-moving CTAs fill those sectors sooner: 3 per SM measured best on the
+    // 11520-column strips of config 3 (profiles/r01_v11_hint_sweep.txt), the full wave on config 2.
+    const int hw_occ = occ;
+    if (tiles_x > 36 && occ > 3) occ = 3;
+    if (const char *ev = getenv("LM_BEV_BIN_CTAS_PER_SM")) {      // tuning knob, 1 .. what the hardware holds
         const int v = atoi(ev);
-        if (v >= 1 && v < occ) occ = v;
+        if (v >= 1) occ = v < hw_occ ? v : hw_occ;
     }
     long long grid = (long long)sms * (occ < 1 ? 1 : occ);
     if (grid > bin_ctas_bound(T)) grid = bin_ctas_bound(T);
@@ -1455,7 +1459,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
         ws.region = 1;
         ws.bin_grid = 0;
         if (n_points > 0) {
-            rc = bin_geometry(las ? (const void *)bin_points_las_kernel : (const void *)bin_points_kernel, smem, nb, kp.T, sms, L, &ws, &grid);
+            rc = bin_geometry(las ? (const void *)bin_points_las_kernel : (const void *)bin_points_kernel, smem, nb, kp.T, kp.tiles_x, sms, L, &ws, &grid);
             if (rc) return rc;
         }
         if (stages & LM_STAGE_BIN) {
@@ -1675,7 +1679,7 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
         if (batches > 0) {
             const size_t smem = bin_smem_bytes(kp.T);
             int grid = 0;
-            rc = bin_geometry((const void *)bin_points_batch_kernel, smem, (long long)batches, kp.T, sms, L, &ws, &grid);
+            rc = bin_geometry((const void *)bin_points_batch_kernel, smem, (long long)batches, kp.T, kp.tiles_x, sms, L, &ws, &grid);
             if (rc) return rc;
             bin_points_batch_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, bt, ws);
         }

@@ -14,7 +14,8 @@ any partition of the points merges exactly.
   (``batch_isend_irecv`` over NCCL/NVLink), are merged into the neighbour's edge band with
   ``lm_bev_acc_merge`` and that band is re-finished with ``lm_bev_finalize`` *before*
   quantising to u8.
-* Mosaic gather: ``all_gather`` of the finished strips (equal strips) -- 398 MB for config 3.
+* Mosaic gather: the finished strips are gathered on one rank (``gather``, what an offline writer needs)
+  or on all of them (``all_gather``) -- 398 MB for config 3.
 
 The arithmetic back end is injected so that the host logic is testable on CPU with gloo
 (tests pass an oracle-backed back end); the product back end is ``CudaBackend``.
@@ -106,11 +107,12 @@ class StripRasterizer:
     """One rank's part of a strip-sharded rasterisation."""
 
     def __init__(self, spec: BevSpec, max_points: int, halo: int = 64, group=None, backend=None,
-                 device: Optional[torch.device | str] = None, align: int = 128):
+                 device: Optional[torch.device | str] = None, align: int = 128, gather_root: Optional[int] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.spec = spec
+        self.gather_root = gather_root          # step(): None = mosaic on every rank, r = on rank r only
         self.plan = make_plan(spec, self.rank, self.world, halo, align)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.backend = backend if backend is not None else CudaBackend(self.device)
@@ -198,15 +200,23 @@ class StripRasterizer:
             self._comm_stream.wait_event(ready)
             if self.need_acc:
                 self._exchange_and_merge(out)
-            self._mosaics[k] = self.gather(strip)
+            self._mosaics[k] = self.gather(strip, self.gather_root)
             done = torch.cuda.Event()
             done.record(self._comm_stream)
         self._gather_done[k] = done
         return k
 
-    def mosaic(self, slot: int) -> torch.Tensor:
+    def mosaic(self, slot: int) -> Optional[torch.Tensor]:
+        """The scene's mosaic (None on the ranks a rooted gather leaves empty); the current stream waits
+        for the scene's exchange, merge and gather."""
         torch.cuda.current_stream(self.device).wait_event(self._gather_done[slot])
         return self._mosaics[slot]
+
+    def strip_of(self, slot: int) -> torch.Tensor:
+        """This rank's own finished strip of the scene in ``slot`` (halo rows cut off, edge bands merged)."""
+        torch.cuda.current_stream(self.device).wait_event(self._gather_done[slot])
+        p = self.plan
+        return self._outs[slot]["image"][p.top:self.local_spec.height - p.bottom]
 
     def flush(self) -> None:
         for ev in self._gather_done:
@@ -217,20 +227,38 @@ class StripRasterizer:
         return r if self.group is None else dist.get_global_rank(self.group, r)
 
     # -- mosaic -----------------------------------------------------------------------------
-    def gather(self, strip: torch.Tensor) -> torch.Tensor:
-        """All ranks get the assembled [H, W, C] mosaic."""
+    def gather(self, strip: torch.Tensor, root: Optional[int] = None) -> Optional[torch.Tensor]:
+        """Assemble the [H, W, C] mosaic from the finished strips.  ``root=None``: every rank gets it
+        (all-gather); ``root=r``: only rank ``r`` does (gather: the other ranks send their strip once and
+        return None -- 1/world of the all-gather's traffic, which is what an offline writer needs)."""
         if self.world == 1:
             return strip
         rows = [b - a for a, b in self.plan.bounds]
         mx = max(rows)
         C = strip.shape[2]
         W = strip.shape[1]
-        if all(r == mx for r in rows):
-            mosaic = torch.empty((self.spec.height, W, C), dtype=strip.dtype, device=strip.device)
-            dist.all_gather_into_tensor(mosaic, strip.contiguous(), group=self.group)
+        equal = all(r == mx for r in rows)
+        if root is None:
+            if equal:
+                mosaic = torch.empty((self.spec.height, W, C), dtype=strip.dtype, device=strip.device)
+                dist.all_gather_into_tensor(mosaic, strip.contiguous(), group=self.group)
+                return mosaic
+            pad = torch.zeros((mx, W, C), dtype=strip.dtype, device=strip.device)
+            pad[:strip.shape[0]] = strip
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad, group=self.group)
+            return torch.cat([parts[k][:rows[k]] for k in range(self.world)], dim=0)
+        if not 0 <= root < self.world:
+            raise ValueError(f"gather: root {root} outside the group of {self.world}")
+        is_root = self.rank == root
+        if equal:
+            mosaic = torch.empty((self.spec.height, W, C), dtype=strip.dtype, device=strip.device) if is_root else None
+            # the strips land in place: row blocks of the mosaic are contiguous
+            parts = list(mosaic.split(mx, dim=0)) if is_root else None
+            dist.gather(strip.contiguous(), parts, dst=self._peer(root), group=self.group)
             return mosaic
         pad = torch.zeros((mx, W, C), dtype=strip.dtype, device=strip.device)
         pad[:strip.shape[0]] = strip
-        parts = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(parts, pad, group=self.group)
-        return torch.cat([parts[k][:rows[k]] for k in range(self.world)], dim=0)
+        parts = [torch.empty_like(pad) for _ in range(self.world)] if is_root else None
+        dist.gather(pad, parts, dst=self._peer(root), group=self.group)
+        return torch.cat([parts[k][:rows[k]] for k in range(self.world)], dim=0) if is_root else None

@@ -39,8 +39,18 @@ def _worker(rank, world, port, q):
         slots = [sr.step(mine) for _ in range(3)]
         piped = sr.mosaic(slots[-1]).clone()
         sr.flush()
+        # mosaic gathered on one rank only, direct and through the pipelined form
+        rooted = sr.gather(strip, root=1)
+        ok_root = bool(torch.equal(rooted, one)) if rank == 1 else rooted is None
+        sr2 = StripRasterizer(spec, len(cloud), halo=64, align=32, gather_root=0)
+        mine2 = torch.from_numpy(np.ascontiguousarray(cloud[coarse_strip_of(cloud[:, 0] + jitter, spec, sr2.plan.bounds) == rank])).cuda()
+        s2 = [sr2.step(mine2) for _ in range(3)]
+        m2 = sr2.mosaic(s2[-1])
+        a, b = sr2.plan.strip
+        ok_root = ok_root and (bool(torch.equal(m2, one)) if rank == 0 else m2 is None) and bool(torch.equal(sr2.strip_of(s2[-1]), one[a:b]))
+        sr2.flush()
         torch.cuda.synchronize()
-        ok = bool(torch.equal(mosaic, one)) and bool(torch.equal(piped, one)) and slots == [0, 1, 0]
+        ok = bool(torch.equal(mosaic, one)) and bool(torch.equal(piped, one)) and slots == [0, 1, 0] and ok_root
         q.put((rank, ok, int(mine.shape[0])))
     finally:
         dist.destroy_process_group()

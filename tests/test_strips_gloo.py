@@ -62,6 +62,10 @@ def _worker(rank, world, port, halo, q):
         r0, r1 = sr.plan.strip
         ok_strip = np.array_equal(strip.numpy(), want[r0:r1])
         ok_mosaic = np.array_equal(mosaic.numpy(), want)
+        # gather on one rank only (what an offline writer needs): the others send and get None
+        root = world - 1
+        rooted = sr.gather(strip, root=root)
+        ok_mosaic = ok_mosaic and (np.array_equal(rooted.numpy(), want) if rank == root else rooted is None)
         q.put((rank, ok_strip, ok_mosaic, int(mine.shape[0])))
     finally:
         dist.destroy_process_group()
