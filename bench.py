@@ -75,7 +75,8 @@ def cpu_rasterize_timed(cloud, spec, processes, reps):
     from oracle import bev_oracle as O
     n = len(cloud)
     P = max(1, processes)
-    ranges = O.scan_point_ranges(n, spec, P)
+    roads = max(1, int(round(spec.width * spec.img_reso[1] / 57.6)))     # synth.make_cloud's default
+    ranges = O.scan_point_ranges(n, spec, P, roads=roads)
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -85,12 +86,25 @@ def cpu_rasterize_timed(cloud, spec, processes, reps):
 
 
 def cpu_sample(spec, n_sample, n_total, seed_rank=0):
-    """A bounded sample of the same workload: the first rows of the scene at the same density."""
+    """A bounded sample of the same workload at the workload's own density.  One-road scenes (config 2):
+    the first rows.  Multi-road scenes (config 3 geometry): a rank's 1440 rows of the first roads, so that
+    the pool's row strips stay long compared with the +-1 m scan jitter, as they are at full size.
+    -> (window spec, cloud, description)"""
     from lanemapping_b200.synth import make_cloud
-    frac_rows = max(128, int(round(spec.height * n_sample / n_total / 128)) * 128)
-    frac_rows = min(frac_rows, spec.height)
-    sub = spec.window(0, frac_rows)
-    return sub, make_cloud(n_sample, sub, order="scan", seed=2021 + seed_rank)
+    density = n_total / spec.cells
+    if spec.width <= 2 * 1152:
+        rows = max(128, int(round(spec.height * n_sample / n_total / 128)) * 128)
+        rows = min(rows, spec.height)
+        sub = spec.window(0, rows)
+    else:
+        rows = min(spec.height, 1440)
+        k = int(round(n_sample / (density * rows * 1152)))
+        k = min(max(k, 1), spec.width // 1152)
+        sub = spec.window(0, rows, 0, k * 1152)
+        n_sample = int(density * rows * k * 1152)
+    cloud = make_cloud(n_sample, sub, order="scan", seed=2021 + seed_rank)
+    what = f"{n_sample} points = rows [0, {sub.height}) x columns [0, {sub.width}) of the workload at full density"
+    return sub, cloud, what
 
 
 def run_reference(args):
@@ -99,7 +113,8 @@ def run_reference(args):
         return 0
     spec, n_full, name = workload(args.gpus, 0, args.points)
     n_sample = min(n_full, args.cpu_points)
-    sub, cloud = cpu_sample(spec, n_sample, n_full * args.gpus)
+    sub, cloud, what = cpu_sample(spec, n_sample, n_full * args.gpus)
+    n_sample = len(cloud)
     P = os.cpu_count() or 1
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_rasterize_timed(cloud, sub, P, 1)
@@ -109,8 +124,7 @@ def run_reference(args):
         cpu_rasterize_timed(cloud, sub, P, 1)
     dt = (time.perf_counter() - t0) / steps
     v = n_sample / dt / 1e6
-    sample = (f"{n_sample} points = first {sub.height} rows of the workload at full density; numpy oracle "
-              f"(floor keys, bincount, maximum.at) over multiprocessing.Pool({P}) row strips")
+    sample = f"{what}; numpy oracle (floor keys, bincount, maximum.at) over multiprocessing.Pool({P}) row strips"
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
@@ -214,11 +228,11 @@ def run_ours(args):
     if args.gpus == 1 and rank == 0 and not args.no_cpu_baseline:
         P = os.cpu_count() or 1
         n_sample = min(n_pts, args.cpu_points)
-        sub, sample_cloud = cpu_sample(spec, n_sample, n_pts)
+        sub, sample_cloud, what = cpu_sample(spec, n_sample, n_pts)
+        n_sample = len(sample_cloud)
         dt = cpu_rasterize_timed(sample_cloud, sub, P, 2)
         cpu_baseline = {"value": round(n_sample / dt / 1e6, 3), "unit": UNIT, "cores": P, "kind": "port",
-                        "sample": f"{n_sample} points = first {sub.height} rows of the workload at full density, "
-                                  f"numpy oracle over multiprocessing.Pool({P}) row strips, best of 2"}
+                        "sample": f"{what}, numpy oracle over multiprocessing.Pool({P}) row strips, best of 2"}
         try:      # for scale: the plain-C restatement of the same spec, one scalar loop on one core
             from oracle import c_oracle as CO
             m = min(len(sample_cloud), 10_000_000)

@@ -166,26 +166,45 @@ def _pool_init(pts):
 
 
 def _pool_strip(args):
-    spec, r0, r1, lo, hi = args
+    spec, r0, r1, ranges = args
     sub = spec.window(r0, r1)
-    return r0, r1, rasterize(_POOL_PTS[lo:hi], sub)
+    if len(ranges) == 1:
+        pts = _POOL_PTS[ranges[0][0]:ranges[0][1]]
+    else:
+        pts = np.concatenate([_POOL_PTS[lo:hi] for lo, hi in ranges], axis=0)
+    return r0, r1, rasterize(pts, sub)
 
 
-def scan_point_ranges(n, spec, processes, margin_m=2.5):
-    """Point index ranges per row strip for a single-road scan-ordered cloud (synth.make_cloud,
-    order='scan': along-track position grows linearly with the index, +-1 m jitter): the strip's
-    own share of the indices widened by ``margin_m`` metres of track on both sides."""
+def scan_point_ranges(n, spec, processes, margin_m=2.5, roads=1):
+    """Point index ranges per row strip for a scan-ordered cloud (synth.make_cloud, order='scan': the
+    cloud is the concatenation of ``roads`` scans, in each of which the along-track position grows
+    linearly with the index, +-1 m jitter): per road, the strip's own share of the indices widened by
+    ``margin_m`` metres of track on both sides.  -> one list of (lo, hi) per strip."""
     H = spec.height
     P = max(1, int(processes))
+    roads = max(1, int(roads))
     edges = [H * k // P for k in range(P + 1)]
-    margin = int(margin_m / (H * spec.img_reso[0]) * n) + 1
-    return [(max(0, int(edges[k] / H * n) - margin), min(n, int(edges[k + 1] / H * n) + margin)) for k in range(P)]
+    per_road = n / roads
+    margin = int(margin_m / (H * spec.img_reso[0]) * per_road) + 1
+    out = []
+    for k in range(P):
+        rs = []
+        for r in range(roads):
+            base = r * per_road
+            lo = max(0, int(base + edges[k] / H * per_road) - margin)
+            hi = min(n, int(base + edges[k + 1] / H * per_road) + margin + 2)
+            if rs and lo <= rs[-1][1]:          # overlapping windows of neighbouring roads: one interval,
+                rs[-1] = (rs[-1][0], max(hi, rs[-1][1]))     # so that no point is taken twice by one strip
+            elif hi > lo:
+                rs.append((lo, hi))
+        out.append(rs)
+    return out
 
 
 def rasterize_pool(pts, spec, processes, point_ranges=None):
     """Row-strip parallel rasterise with ``processes`` forked workers.
 
-    point_ranges: optional list of (lo, hi) point index ranges per strip (for
+    point_ranges: optional, per strip either one (lo, hi) point index range or a list of them (for
     along-track-ordered clouds, with a margin); default = every strip scans all points.
     """
     import multiprocessing as mp
@@ -196,8 +215,10 @@ def rasterize_pool(pts, spec, processes, point_ranges=None):
     for k in range(P):
         if edges[k + 1] <= edges[k]:
             continue
-        lo, hi = (0, len(pts)) if point_ranges is None else point_ranges[k]
-        jobs.append((spec, edges[k], edges[k + 1], lo, hi))
+        rs = [(0, len(pts))] if point_ranges is None else point_ranges[k]
+        if rs and not isinstance(rs[0], (tuple, list)):
+            rs = [tuple(rs)]
+        jobs.append((spec, edges[k], edges[k + 1], [(int(a), int(b)) for a, b in rs]))
     img = np.zeros((H, spec.width, len(spec.channels)), dtype=np.uint8)
     c16 = np.zeros((H, spec.width), dtype=np.uint16) if spec.count16 else None
     ctx = mp.get_context("fork")

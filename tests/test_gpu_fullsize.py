@@ -1,10 +1,10 @@
 """GPU parity at BASELINE.json's FULL sizes (configs[1] and configs[3]: 10^8 points each).
 
-The numpy oracle needs about a minute for 10^8 points on one core, so it runs over all host cores
-(oracle.rasterize_pool, row strips -- the same split the CPU arm of bench.py times) and the whole
-raster is compared bit for bit.  Beside that, size-independent properties: conservation of the
-in-grid point count (kernel statistics == a host recount of the keys) and agreement of the two
-independent CUDA algorithms (binned pipeline == global-atomics path)."""
+The numpy oracle needs minutes for 10^8 points on one core, so the whole raster is compared bit for
+bit with the plain-C restatement (oracle/bev_oracle.c, seconds; tests/test_c_oracle.py holds the two
+restatements equal).  Beside that, size-independent properties: conservation of the in-grid point
+count (kernel statistics == the numpy oracle's recount of the keys == the C oracle's) and agreement
+of the two independent CUDA algorithms (binned pipeline == global-atomics path)."""
 import os
 
 import numpy as np
@@ -13,6 +13,7 @@ import torch
 
 from lanemapping_b200.synth import config_spec, make_cloud
 from oracle import bev_oracle as O
+from oracle import c_oracle as C
 
 pytestmark = pytest.mark.gpu
 
@@ -48,9 +49,9 @@ def bev(native_lib):
 def test_full_size_config_is_bit_exact(bev, cfg):
     spec, n = config_spec(cfg)
     cloud = make_cloud(n, spec, order="scan")
-    P = os.cpu_count() or 1
-    want = O.rasterize_pool(cloud, spec, P, point_ranges=O.scan_point_ranges(n, spec, P))
+    want = C.rasterize(cloud, spec)
     n_valid = _host_valid_count(cloud, spec)
+    assert want["n_valid"] == n_valid
     pts = torch.from_numpy(cloud).cuda()
     outputs = ("image", "count16") if spec.count16 else ("image",)
     got, st = _run(bev, pts, spec, "binned", outputs, n)

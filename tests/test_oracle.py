@@ -152,3 +152,17 @@ def test_pool_variant_matches_single_thread():
     one = O.rasterize(cloud, spec)
     par = O.rasterize_pool(cloud, spec, processes=3)
     assert np.array_equal(one["image"], par["image"]) and np.array_equal(one["count16"], par["count16"])
+
+
+@pytest.mark.parametrize("height,width,n,procs", [(600, 4608, 300_001, 7), (2304, 1152, 400_003, 5)])
+def test_pool_with_scan_point_ranges_matches_single_thread(height, width, n, procs):
+    # the bounded index ranges the CPU arm of bench.py hands to its strips (one or several roads
+    # scanned one after the other) must lose no point and take none twice
+    spec = BevSpec(height, width, local_min_ele=-8.0)
+    cloud = make_cloud(n, spec, seed=3, order="scan")
+    roads = max(1, int(round(width * spec.img_reso[1] / 57.6)))
+    ranges = O.scan_point_ranges(n, spec, procs, roads=roads)
+    assert len(ranges) == procs and all(a < b for rs in ranges for a, b in rs)
+    assert all(rs[i][1] < rs[i + 1][0] for rs in ranges for i in range(len(rs) - 1))     # disjoint within a strip
+    par = O.rasterize_pool(cloud, spec, procs, point_ranges=ranges)
+    assert np.array_equal(O.rasterize(cloud, spec)["image"], par["image"])
