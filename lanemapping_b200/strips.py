@@ -209,8 +209,12 @@ class StripRasterizer:
     def mosaic(self, slot: int) -> Optional[torch.Tensor]:
         """The scene's mosaic (None on the ranks a rooted gather leaves empty); the current stream waits
         for the scene's exchange, merge and gather."""
-        torch.cuda.current_stream(self.device).wait_event(self._gather_done[slot])
-        return self._mosaics[slot]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._gather_done[slot])
+        m = self._mosaics[slot]
+        if m is not None:
+            m.record_stream(cur)        # allocated on the side stream, read on this one
+        return m
 
     def strip_of(self, slot: int) -> torch.Tensor:
         """This rank's own finished strip of the scene in ``slot`` (halo rows cut off, edge bands merged)."""
