@@ -152,6 +152,65 @@ class BevRasterizer:
             raise RuntimeError("liblm_bev: a cell received >= 2^24 points; u32 sums may have wrapped")
 
 
+class PipelinedRasterizer:
+    """Throughput mode for a stream of equally-shaped scenes -- EXPERIMENTAL, not yet measured
+    (DESIGN.md section 9): ``bin_points`` of scene k+1 runs on one stream while ``index`` +
+    ``reduce_tiles`` of scene k run on another, through the stage-split C-ABI entry.  ``bin_points`` is
+    HBM-bound and ``reduce_tiles`` shared-memory-atomic-bound, so the two can share the SMs; for them to be
+    co-resident the grids have to leave room for each other (``LM_BEV_BIN_CTAS_PER_SM=2``,
+    ``LM_BEV_RED_CTAS_PER_SM=1`` fit the register file and shared memory of an SM together).
+    Two workspaces and two output sets: at most two scenes are in flight, slot k % 2 is reused by
+    scene k + 2."""
+
+    def __init__(self, spec: BevSpec, max_points: int, device: torch.device | str = "cuda",
+                 outputs: Iterable[str] = ("image",)):
+        self.rasters = [BevRasterizer(spec, max_points, device=device, algo="binned", outputs=outputs) for _ in range(2)]
+        self.device = self.rasters[0].device
+        self.outs = [r.alloc_outputs() for r in self.rasters]
+        self.s_bin = torch.cuda.Stream(self.device)
+        self.s_red = torch.cuda.Stream(self.device)
+        self._done = [None, None]
+        self._k = 0
+
+    def submit(self, points: torch.Tensor) -> int:
+        """Enqueue one scene; returns its slot.  ``points`` must stay unchanged until the scene is done."""
+        slot = self._k % 2
+        self._k += 1
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.s_bin.wait_event(ready)                       # the caller's stream produced the points
+        if self._done[slot] is not None:
+            self.s_bin.wait_event(self._done[slot])        # workspace and outputs of scene k - 2 are free
+        r, out = self.rasters[slot], self.outs[slot]
+        points.record_stream(self.s_bin)
+        r(points, out=out, stream=self.s_bin, stages=_cabi.STAGE_BIN)
+        binned = torch.cuda.Event()
+        binned.record(self.s_bin)
+        self.s_red.wait_event(binned)
+        r(points, out=out, stream=self.s_red, stages=_cabi.STAGE_INDEX)
+        r(points, out=out, stream=self.s_red, stages=_cabi.STAGE_REDUCE)
+        done = torch.cuda.Event()
+        done.record(self.s_red)
+        self._done[slot] = done
+        return slot
+
+    def result(self, slot: int) -> Dict[str, torch.Tensor]:
+        """The scene's outputs; the current stream waits for its reduce."""
+        torch.cuda.current_stream(self.device).wait_event(self._done[slot])
+        return self.outs[slot]
+
+    def flush(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for d in self._done:
+            if d is not None:
+                cur.wait_event(d)
+
+    def check_device_errors(self) -> None:
+        for r in self.rasters:
+            r.check_device_errors()
+
+
 class BatchRasterizer:
     """B equally-shaped rasters per call (``lm_bev_rasterize_batch``): the samples of a DataLoader
     batch are stacked along the rows inside the library and share one set of launches.

@@ -73,6 +73,11 @@ constexpr int IDX_ID_BITS = 23;                  // index entry: piece id | (cou
 #ifndef LM_BIN_MIN_CTAS
 #define LM_BIN_MIN_CTAS 4
 #endif
+#ifndef LM_BIN_STAGES
+#define LM_BIN_STAGES 2      // TMA stage buffers of bin_points (tuning builds: 3 or 4 keep more loads in flight per CTA)
+#endif
+constexpr int BIN_STAGES = LM_BIN_STAGES;
+static_assert(BIN_STAGES >= 2 && BIN_STAGES <= 4, "bin_points stages its batches through 2..4 buffers");
 constexpr int BIN_THREADS = LM_BIN_THREADS;
 constexpr int BIN_PPT = LM_BIN_PPT;       // points per thread per batch
 constexpr int BIN_BATCH = BIN_THREADS * BIN_PPT;
@@ -390,16 +395,24 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
     const int T = kp.T;
     // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u16
     uint32_t sm_stage = smem_u32(smem_raw);
-    uint32_t sm_pos = sm_stage + 2u * stage_bytes;
+    uint32_t sm_pos = sm_stage + (uint32_t)BIN_STAGES * stage_bytes;
     uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
     // keep the three bases in registers: without this the compiler re-derives them (window base +
     // offsets, ~5 instructions) at every use because they are cheap to rematerialise
     asm volatile("" : "+r"(sm_stage), "+r"(sm_pos), "+r"(sm_slot));
     __shared__ uint32_t s_next;                                              // next local chunk id of this CTA's region
-    __shared__ __align__(8) uint64_t s_bar[2];                               // TMA completion barriers
+    __shared__ __align__(8) uint64_t s_bar[BIN_STAGES];                      // TMA completion barriers
 
     const int tid = threadIdx.x;
+#if LM_BIN_STAGES == 2
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_next = 1u; }
+#else
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < BIN_STAGES; ++b) mbar_init(&s_bar[b], 1);
+        s_next = 1u;
+    }
+#endif
     const uint32_t sm_next = smem_u32(&s_next);
     const uint32_t region_base = blockIdx.x * ws.region;
     for (int t = tid; t < T; t += BIN_THREADS) sts_u32(sm_pos + 4u * t, 0u);
@@ -428,16 +441,32 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
     // bytes past its last record -- the caller's buffer is padded, lm_las.h)
     auto batch_bytes = [&](uint32_t np) -> uint32_t { return LAS ? (np * rec_bytes + 15u) & ~15u : np * 16u; };
     int samp = 0, samp_pf = 0;                                               // sample cursors: compute / prefetch (thread 0)
+#if LM_BIN_STAGES == 2
     if (tid == 0 && my_batches > 0) {
         uint32_t np;
         const void *src = batch_src(0, samp_pf, np);
         if (kp.stream_hint & 1) bulk_load_stream(smem_raw, src, batch_bytes(np), &s_bar[0]);
         else bulk_load(smem_raw, src, batch_bytes(np), &s_bar[0]);
     }
+#else
+    // the first BIN_STAGES - 1 batches start flying before the loop
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < BIN_STAGES - 1; ++b) {
+            if (b < my_batches) {
+                uint32_t np;
+                const void *src = batch_src(b, samp_pf, np);
+                if (kp.stream_hint & 1) bulk_load_stream(smem_raw + (uint32_t)b * stage_bytes, src, batch_bytes(np), &s_bar[b]);
+                else bulk_load(smem_raw + (uint32_t)b * stage_bytes, src, batch_bytes(np), &s_bar[b]);
+            }
+        }
+    }
+#endif
     Geo geo = geo_of(kp);
     int row_shift = 0;                                                       // first row of the sample in the stacked raster
 
     for (int k = 0; k < my_batches; ++k) {
+#if LM_BIN_STAGES == 2
         const uint32_t buf = (uint32_t)k & 1u;
         // the NEXT batch starts flying now, into the buffer that was consumed one batch ago
         if (tid == 0 && k + 1 < my_batches) {
@@ -446,13 +475,28 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
             if (kp.stream_hint & 1) bulk_load_stream(smem_raw + (buf ^ 1u) * stage_bytes, src, batch_bytes(np), &s_bar[buf ^ 1u]);
             else bulk_load(smem_raw + (buf ^ 1u) * stage_bytes, src, batch_bytes(np), &s_bar[buf ^ 1u]);
         }
+#else
+        const uint32_t buf = (uint32_t)k % (uint32_t)BIN_STAGES;
+        // batch k + BIN_STAGES - 1 starts flying now, into the buffer that was consumed one batch ago
+        if (tid == 0 && k + BIN_STAGES - 1 < my_batches) {
+            const uint32_t nbuf = (uint32_t)(k + BIN_STAGES - 1) % (uint32_t)BIN_STAGES;
+            uint32_t np;
+            const void *src = batch_src(k + BIN_STAGES - 1, samp_pf, np);
+            if (kp.stream_hint & 1) bulk_load_stream(smem_raw + nbuf * stage_bytes, src, batch_bytes(np), &s_bar[nbuf]);
+            else bulk_load(smem_raw + nbuf * stage_bytes, src, batch_bytes(np), &s_bar[nbuf]);
+        }
+#endif
         uint32_t npts;
         batch_src(k, samp, npts);
         if (BATCHED) {
             geo = Geo{bt.off0[samp], bt.off1[samp], bt.zmin[samp], bt.row0[samp], bt.col0[samp], bt.bH};
             row_shift = samp * bt.bH;
         }
+#if LM_BIN_STAGES == 2
         mbar_wait(&s_bar[buf], ((uint32_t)k >> 1) & 1u);     // this batch's records have landed
+#else
+        mbar_wait(&s_bar[buf], ((uint32_t)k / (uint32_t)BIN_STAGES) & 1u);
+#endif
         float4 p[BIN_PPT];
         const uint32_t my_stage = sm_stage + buf * stage_bytes + (uint32_t)tid * rec_bytes;
 #pragma unroll
@@ -1163,7 +1207,7 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     return k;
 }
 
-size_t bin_smem_bytes(int T) { return 2 * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * (4 + 2 * NSLOT); }
+size_t bin_smem_bytes(int T) { return BIN_STAGES * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * (4 + 2 * NSLOT); }
 
 // chunks per bin CTA when `grid` CTAs share `nb` batches: the chunks its points can fill, one open
 // chunk per tile, and the unused local id 0
@@ -1291,6 +1335,10 @@ cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sm
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK>, RED_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
+    if (const char *ev = getenv("LM_BEV_RED_CTAS_PER_SM")) {      // tuning knob: leave room for a concurrent bin_points
+        const int v = atoi(ev);
+        if (v >= 1 && v < occ) occ = v;
+    }
     const int grid = kp.T < sms * occ ? kp.T : sms * occ;
     reduce_tiles_kernel<MASK><<<grid, RED_THREADS, smem, st>>>(kp, ws, o);
     return cudaGetLastError();
@@ -1453,7 +1501,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
         kp.band = banded ? out->acc_band : 0;
         cudaError_t e = cudaSuccess;
         const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
-        const size_t smem = las ? 2 * (size_t)las_stage_bytes((uint32_t)las->record_length, BIN_BATCH) + (size_t)kp.T * (4 + 2 * NSLOT)
+        const size_t smem = las ? BIN_STAGES * (size_t)las_stage_bytes((uint32_t)las->record_length, BIN_BATCH) + (size_t)kp.T * (4 + 2 * NSLOT)
                                 : bin_smem_bytes(kp.T);
         int grid = 0;
         ws.region = 1;

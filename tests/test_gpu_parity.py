@@ -250,3 +250,25 @@ def test_exact_mean_exhaustive(bev, native_lib):
     torch.cuda.synchronize()
     bad, n = (int(v) for v in out.cpu())
     assert n == sum(255 * c + 1 for c in range(1, 4096)) and bad == 0
+
+
+@pytest.mark.skipif(__import__("os").environ.get("LM_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental overlap mode (DESIGN.md section 9): opt in with LM_TEST_EXPERIMENTAL=1")
+def test_pipelined_rasterizer_matches_oracle(bev):
+    # bin_points of scene k+1 on one stream, index + reduce_tiles of scene k on another: every scene's
+    # raster must still be the oracle's, whatever the interleaving
+    spec = BevSpec(2304, 1152, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(2304, 1152)))
+    clouds = [make_cloud(1_500_000 + 100_000 * i, spec, seed=40 + i, order="scan" if i % 2 == 0 else "shuffled") for i in range(5)]
+    dev = [torch.from_numpy(c).cuda() for c in clouds]
+    pr = bev.PipelinedRasterizer(spec, max(len(c) for c in clouds))
+    got = [pr.submit(d) for d in dev]
+    # only the last two scenes are still in their slots; replay the earlier ones one at a time
+    want = [O.rasterize(c, spec)["image"] for c in clouds]
+    assert np.array_equal(pr.result(got[-1])["image"].cpu().numpy(), want[-1])
+    assert np.array_equal(pr.result(got[-2])["image"].cpu().numpy(), want[-2])
+    for i in range(3):
+        s = pr.submit(dev[i])
+        assert np.array_equal(pr.result(s)["image"].cpu().numpy(), want[i])
+    pr.flush()
+    torch.cuda.synchronize()
+    pr.check_device_errors()
