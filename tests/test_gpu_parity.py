@@ -252,21 +252,21 @@ def test_exact_mean_exhaustive(bev, native_lib):
     assert n == sum(255 * c + 1 for c in range(1, 4096)) and bad == 0
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LM_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental overlap mode (DESIGN.md section 9): opt in with LM_TEST_EXPERIMENTAL=1")
 def test_pipelined_rasterizer_matches_oracle(bev):
-    # bin_points of scene k+1 on one stream, index + reduce_tiles of scene k on another: every scene's
-    # raster must still be the oracle's, whatever the interleaving
-    spec = BevSpec(2304, 1152, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(2304, 1152)))
-    clouds = [make_cloud(1_500_000 + 100_000 * i, spec, seed=40 + i, order="scan" if i % 2 == 0 else "shuffled") for i in range(5)]
+    # two-stream mode (bev.PipelinedRasterizer): bin_points of scene k+1 on one stream, index + reduce_tiles of
+    # scene k on another -- every scene's raster must still be the oracle's, whatever the interleaving
+    # (the same scenes as tools/try_pipeline.py, checked here against the C restatement)
+    from oracle import c_oracle as CO
+    spec = BevSpec(1152, 1152, local_min_ele=default_min_ele(BevSpec(1152, 1152)))
+    clouds = [make_cloud(800_000 + 50_000 * i, spec, seed=70 + i, order="scan" if i % 2 else "shuffled") for i in range(4)]
+    want = [CO.rasterize(c, spec)["image"] for c in clouds]
     dev = [torch.from_numpy(c).cuda() for c in clouds]
     pr = bev.PipelinedRasterizer(spec, max(len(c) for c in clouds))
-    got = [pr.submit(d) for d in dev]
-    # only the last two scenes are still in their slots; replay the earlier ones one at a time
-    want = [O.rasterize(c, spec)["image"] for c in clouds]
-    assert np.array_equal(pr.result(got[-1])["image"].cpu().numpy(), want[-1])
-    assert np.array_equal(pr.result(got[-2])["image"].cpu().numpy(), want[-2])
-    for i in range(3):
+    slots = [pr.submit(d) for d in dev]
+    assert slots == [0, 1, 0, 1]
+    for i in (2, 3):                       # the last two scenes are still in their slots
+        assert np.array_equal(pr.result(slots[i])["image"].cpu().numpy(), want[i])
+    for i in (0, 1):
         s = pr.submit(dev[i])
         assert np.array_equal(pr.result(s)["image"].cpu().numpy(), want[i])
     pr.flush()
