@@ -12,7 +12,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "liblm_bev.so")
+# LM_BEV_LIB: load / build another file name inside csrc/ (A/B tuning builds side by side); the default is the product
+LIB_PATH = os.path.join(CSRC, os.path.basename(os.environ.get("LM_BEV_LIB", "") or "liblm_bev.so"))
 SOURCES = [os.path.join(CSRC, "lm_bev.cu"), os.path.join(CSRC, "lm_post.cu")]
 HEADERS = [os.path.join(ROOT, "include", h) for h in ("lm_bev.h", "lm_las.h", "lm_post.h")] + \
           [os.path.join(CSRC, h) for h in ("lm_dev.cuh", "lm_host.h")]

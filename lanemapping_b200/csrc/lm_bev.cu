@@ -1298,6 +1298,9 @@ int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles
     if (smem > 220 * 1024) return fail(LM_ERR_UNSUPPORTED, "%zu bytes of shared memory per bin CTA: too many tiles / too long records", smem);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
+    // the same (maximal) shared-memory carve-out for every kernel of the pipeline: an SM only switches its L1/shared
+    // split when idle, so kernels with different carve-outs never share an SM (no bin/reduce overlap)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BIN_THREADS, smem);
     if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
@@ -1331,6 +1334,7 @@ cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sm
     const size_t smem = (size_t)popc6(MASK) * ((size_t)TILE_W << kp.tile_h_log2) * 4;
     cudaError_t e = cudaFuncSetAttribute(reduce_tiles_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(reduce_tiles_kernel<MASK>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK>, RED_THREADS, smem);
     if (e != cudaSuccess) return e;

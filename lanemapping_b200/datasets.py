@@ -103,16 +103,84 @@ def make_onthefly_dataset(base, points_dir: str = "crop_points", param_dir: str 
     return LaserLaneProposalOnTheFly
 
 
+class PointBatch:
+    """The ragged clouds of one batch, packed: ``points`` float32 [sum N_i, 4] + ``offsets`` int64 [B + 1]
+    (host).  It is deliberately NOT a list of tensors: the reference's ``Runner.to_cuda`` turns a list of
+    tensors into ``torch.cat([t.unsqueeze(0) ...])`` (reference baseline/engine/runner.py:139-142), which
+    raises for clouds of different lengths.  A non-list entry goes through ``batch[k].cuda(non_blocking=True)``
+    (runner.py:149), which this class implements; ``pin_memory()`` is what ``DataLoader(pin_memory=True)``
+    (reference baseline/datasets/registry.py:54-56) calls on custom batch types; ``nn.DataParallel`` on the
+    reference's single visible device (``CUDA_VISIBLE_DEVICES='0'``, train_gpu_0.py:6-7) hands a non-tensor
+    object to the replica unchanged.  For DataParallel over SEVERAL devices use ``collate_points_padded``."""
+
+    def __init__(self, points: torch.Tensor, offsets):
+        self.points = points
+        self.offsets = [int(o) for o in offsets]
+        if self.offsets[0] != 0 or self.offsets[-1] != int(points.shape[0]) or \
+                any(a > b for a, b in zip(self.offsets, self.offsets[1:])):
+            raise ValueError("PointBatch: offsets must rise from 0 to len(points)")
+
+    @classmethod
+    def from_list(cls, clouds: List[torch.Tensor]) -> "PointBatch":
+        offs = [0]
+        for c in clouds:
+            if c.ndim != 2 or c.shape[1] != 4:
+                raise ValueError("PointBatch: every cloud must be [N, 4] (x, y, z, intensity)")
+            offs.append(offs[-1] + int(c.shape[0]))
+        pts = torch.cat([c.to(torch.float32) for c in clouds], dim=0) if clouds else torch.empty((0, 4))
+        return cls(pts.contiguous(), offs)
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, i: int) -> torch.Tensor:
+        return self.points[self.offsets[i]:self.offsets[i + 1]]
+
+    def clouds(self) -> List[torch.Tensor]:
+        return [self[i] for i in range(len(self))]
+
+    @property
+    def device(self):
+        return self.points.device
+
+    def cuda(self, device=None, non_blocking: bool = False) -> "PointBatch":
+        return PointBatch(self.points.cuda(device, non_blocking=non_blocking), self.offsets)
+
+    def to(self, *a, **k) -> "PointBatch":
+        return PointBatch(self.points.to(*a, **k), self.offsets)
+
+    def pin_memory(self) -> "PointBatch":
+        return PointBatch(self.points.pin_memory(), self.offsets)
+
+
 def collate_points(batch: List[dict]) -> dict:
-    """Collate for variable-length clouds: ``points`` stays a list of tensors (what the reference
-    anticipates with ``pseudo_collate``, reference baseline/datasets/registry.py:58, and what
-    ``Runner.to_cuda`` handles in its list branch, reference baseline/engine/runner.py:139-147);
-    everything else is default-collated."""
+    """Collate for variable-length clouds (``collate_fn=`` of the reference's DataLoader, where it
+    anticipates ``pseudo_collate``: reference baseline/datasets/registry.py:58).  ``points`` becomes ONE
+    ``PointBatch`` -- see there why it must not stay a list of tensors -- and everything else is
+    default-collated, so the unmodified ``Runner.to_cuda`` moves the whole batch."""
     from torch.utils.data import default_collate
-    pts = [b["points"] for b in batch]
+    pts = PointBatch.from_list([b["points"] for b in batch])
     rest = [{k: v for k, v in b.items() if k != "points"} for b in batch]
     out = default_collate(rest)
     out["points"] = pts
+    return out
+
+
+def collate_points_padded(batch: List[dict]) -> dict:
+    """The same batch as dense tensors: ``points`` [B, N_max, 4], padded with NaN records (the rasteriser
+    drops NaN points, spec step 1) + ``points_count`` [B].  Costs the padding in H2D bytes, but every entry
+    splits along dim 0, which is what ``nn.DataParallel`` over several devices (reference
+    baseline/engine/runner.py:103) does to a batch."""
+    from torch.utils.data import default_collate
+    clouds = [b["points"] for b in batch]
+    n_max = max([int(c.shape[0]) for c in clouds] + [1])
+    pts = torch.full((len(clouds), n_max, 4), float("nan"), dtype=torch.float32)
+    for i, c in enumerate(clouds):
+        pts[i, :c.shape[0]] = c
+    rest = [{k: v for k, v in b.items() if k != "points"} for b in batch]
+    out = default_collate(rest)
+    out["points"] = pts
+    out["points_count"] = torch.tensor([int(c.shape[0]) for c in clouds], dtype=torch.int64)
     return out
 
 

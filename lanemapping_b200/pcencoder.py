@@ -71,10 +71,26 @@ class OnTheFlyProjector(nn.Module):
         self.cfg = cfg
         self.projector = BatchProjector(**proj_kwargs)
 
+    @staticmethod
+    def clouds_of(sample) -> List[torch.Tensor]:
+        """The per-sample [N_i, 4] clouds of a batch, whichever collate produced it:
+        ``datasets.PointBatch`` (packed, ``collate_points``), a dense NaN-padded [B, N_max, 4] tensor with
+        ``points_count`` (``collate_points_padded``: the form ``nn.DataParallel`` can split), or a list."""
+        pts = sample["points"]
+        if hasattr(pts, "clouds"):
+            return pts.clouds()
+        if isinstance(pts, torch.Tensor):
+            if pts.ndim != 3 or pts.shape[-1] != 4:
+                raise ValueError("sample['points']: a dense batch must be [B, N_max, 4]")
+            cnt = sample.get("points_count")
+            if cnt is None:
+                return [pts[b] for b in range(pts.shape[0])]        # NaN padding is dropped by the rasteriser
+            return [pts[b, :int(cnt[b])] for b in range(pts.shape[0])]
+        return [p.data if hasattr(p, "data") else p for p in pts]
+
     def forward(self, sample):
         if "proj" not in sample:
-            pts = [p.data if hasattr(p, "data") else p for p in sample["points"]]
-            sample["proj"] = self.projector(pts, sample.get("bev_geom"))
+            sample["proj"] = self.projector(self.clouds_of(sample), sample.get("bev_geom"))
         return self.inner(sample)
 
     def loss(self, *a, **k):

@@ -155,8 +155,8 @@ def test_on_the_fly_projector_matches_png_loader_path(bev, tmp_path):
     ds = CropPoints(str(root), "split.json", "test")
     assert len(ds) == 3 and ds[1]["image_name"] == "000000_0002"
     batch = collate_points([ds[i] for i in range(3)])
-    assert isinstance(batch["points"], list) and batch["bev_geom"].shape == (3, 8)
-    batch["points"] = [p.cuda() for p in batch["points"]]       # what Runner.to_cuda's list branch does
+    assert len(batch["points"]) == 3 and batch["bev_geom"].shape == (3, 8)
+    batch["points"] = batch["points"].cuda(non_blocking=True)    # Runner.to_cuda's non-list branch (tests/test_plugins.py)
 
     class Inner(torch.nn.Module):                                 # stands in for PostProjector2.forward
         def forward(self, sample):
