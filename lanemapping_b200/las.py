@@ -24,6 +24,18 @@ class LasHeader:
     n_points: int
     scale: Tuple[float, float, float]
     offset: Tuple[float, float, float]
+    mins: Tuple[float, float, float] = (float("nan"),) * 3      # header bounds (min x, y, z); NaN if absent
+    maxs: Tuple[float, float, float] = (float("nan"),) * 3
+
+    def bounds_ok(self) -> bool:
+        """Are the header's min/max bounds usable (finite, ordered, not the all-zero of a lazy writer)?"""
+        import math
+        vals = list(self.mins) + list(self.maxs)
+        if not all(math.isfinite(v) for v in vals):
+            return False
+        if any(lo > hi for lo, hi in zip(self.mins, self.maxs)):
+            return False
+        return any(v != 0.0 for v in vals)
 
 
 def read_header(buf: bytes) -> LasHeader:
@@ -44,7 +56,21 @@ def read_header(buf: bytes) -> LasHeader:
             n = n64
     if reclen < 14:
         raise ValueError("LAS record length < 14")
-    return LasHeader((major, minor), offset_to_points, fmt, reclen, int(n), scale, offset)
+    mins = maxs = (float("nan"),) * 3
+    if len(buf) >= 227:                         # max x, min x, max y, min y, max z, min z
+        b = struct.unpack_from("<6d", buf, 179)
+        maxs, mins = (b[0], b[2], b[4]), (b[1], b[3], b[5])
+    return LasHeader((major, minor), offset_to_points, fmt, reclen, int(n), scale, offset, mins, maxs)
+
+
+def world_min(raw: np.ndarray, hdr: LasHeader) -> Tuple[float, float, float]:
+    """Exact minimum of the world coordinates from the int32 X/Y/Z fields of the point block (one
+    strided integer pass, then ONE scale+offset in float64): what a reader falls back to when the
+    header bounds are missing."""
+    n = hdr.n_points
+    ixyz = np.ndarray((n, 3), dtype="<i4", buffer=raw, strides=(hdr.record_length, 4))
+    lo = ixyz.min(axis=0).astype(np.float64) if n else np.zeros(3)
+    return tuple(float(v) for v in lo * np.asarray(hdr.scale) + np.asarray(hdr.offset))
 
 
 def read_las(path: str):

@@ -119,8 +119,100 @@ def test_offline_converter_writes_reference_compatible_files(bev, tmp_path):
     for k, s in enumerate(stems):
         png = np.array(Image.open(os.path.join(tiff, s + ".png")), dtype=np.uint8)
         assert np.array_equal(proj[k].cpu().numpy(), O.proj_from_image(png))      # bit-identical to the PNG path
-    man = json.load(open(os.path.join(param, "181013.manifest.json")))
-    assert man["stems"] == stems and man["n_points"] == n
+    man = json.load(open(os.path.join(param, "181013_road.manifest.json")))       # keyed by the input's own stem
+    assert man["stems"] == stems and man["n_points"] == n and man["source"] == las_path
+    assert man["las_read_offset"] == [533000.0, 3380000.0, 20.0]                   # floor(min) of the data
+
+
+def _write_road_las(path, x0, y0, z_of_x, n, seed, scale=0.001, offset=None, outlier=None, gap=None):
+    from lanemapping_b200 import las
+    rng = np.random.default_rng(seed)
+    x = rng.random(n) * 100.0
+    if gap is not None:                                       # keep points away from a crop edge (cell-exact tests)
+        x = np.where(np.abs(x - gap) < 0.1, x + 1.0, x)
+    world = np.stack([x0 + x, y0 + rng.random(n) * 20.0, z_of_x(x) + 0.01 * rng.standard_normal(n)], axis=1)
+    if outlier is not None:
+        world[0] = (x0 + 5.0, y0 + 5.0, outlier)             # in the first crop
+    inten = rng.integers(500, 40000, n)
+    las.write_las(path, world, inten, scale=(scale,) * 3, offset=offset)
+    return las.read_las(path)
+
+
+def test_offline_converter_files_sharing_six_digits_do_not_collide(bev, tmp_path):
+    """'181013_0130.las' and '181013_0131.las' both suggest sequence id 181013: the driver
+    gives them distinct ids, the manifests are per input file, and forcing the same id raises."""
+    from lanemapping_b200.convert_data import multiprocessing_las_files, rasterize_single_file
+    a, b = str(tmp_path / "181013_0130.las"), str(tmp_path / "181013_0131.las")
+    _write_road_las(a, 1000.0, 2000.0, lambda x: 5.0 + 0 * x, 60_000, 1)
+    _write_road_las(b, 5000.0, 2000.0, lambda x: 7.0 + 0 * x, 50_000, 2)
+    tiff, param = str(tmp_path / "tiff"), str(tmp_path / "param")
+    st = {}
+    stems = multiprocessing_las_files([b, a], tiff, param, num_process=2, stats=st)
+    assert stems == ["181013_0001", "181013_0002", "181014_0001", "181014_0002"]
+    assert st["files"] == 2 and st["points"] == 110_000 and st["crops"] == 4 and st["files_per_s"] > 0
+    assert 0.0 < st["png_share"] < 1.0 and st["devices"]
+    ma = json.load(open(os.path.join(param, "181013_0130.manifest.json")))
+    mb = json.load(open(os.path.join(param, "181013_0131.manifest.json")))
+    assert ma["stems"] == stems[:2] and mb["stems"] == stems[2:] and ma["source"] == a and mb["source"] == b
+    before = {s: os.path.getmtime(os.path.join(tiff, s + ".png")) for s in stems}
+    assert multiprocessing_las_files([a, b], tiff, param, num_process=1) == stems          # both skipped via their manifests
+    assert before == {s: os.path.getmtime(os.path.join(tiff, s + ".png")) for s in stems}
+    with pytest.raises(FileExistsError):                     # the same id for another file: refuse, never overwrite
+        rasterize_single_file(b, tiff, param, seq_id=181013)
+
+
+def test_offline_converter_takes_read_offset_from_the_data(bev, tmp_path):
+    """A LAS writer that leaves the header offset at 0 for UTM-scale coordinates: subtracting only the header
+    offset would leave 3.38e6 m in float32 (ulp 0.25 m against 0.05 m cells).  The converter takes
+    floor(min) of the data instead, writes it into the sidecar, and the raster equals the oracle's on the
+    float64-exact local coordinates."""
+    from lanemapping_b200.convert_data import multiprocessing_las_files
+    path = str(tmp_path / "000042.las")
+    xyz, inten, hdr = _write_road_las(path, 533100.0, 3380200.0, lambda x: 31.0 + 0.01 * x, 200_000, 3,
+                                      scale=0.01, offset=(0.0, 0.0, 0.0))
+    assert hdr.offset == (0.0, 0.0, 0.0)
+    for mode, sub in (("gpu", "g"), ("host", "h")):
+        tiff, param = str(tmp_path / ("tiff" + sub)), str(tmp_path / ("param" + sub))
+        stems = multiprocessing_las_files([path], tiff, param, num_process=1, las_decode=mode, min_ele="file")
+        assert stems == ["000042_0001", "000042_0002"]
+        for k, stem in enumerate(stems):
+            p = sidecar.read_sidecar(os.path.join(param, stem + ".txt"))
+            assert tuple(p.las_read_offset) == tuple(np.floor(xyz.min(axis=0)))
+            local = xyz - np.asarray(p.las_read_offset)
+            pts = np.concatenate([local, inten[:, None]], axis=1).astype(np.float32)
+            spec = BevSpec(1152, 1152, bev_img_offset=(0.0, 0.0), local_min_ele=p.local_min_ele, row0=k * 1152)
+            img = np.array(Image.open(os.path.join(tiff, stem + ".png")), dtype=np.uint8)
+            assert np.array_equal(img, O.rasterize(pts, spec)["image"])
+            assert p.bev_img_offset == (k * 57.6, 0.0)
+
+
+def test_offline_converter_per_crop_min_ele(bev, tmp_path):
+    """A run that climbs 30 m over two crops, with one point 40 m below the road: one local_min_ele per FILE
+    saturates the upper crop (12.75 m of u8 range at 0.05 m); the robust per-crop value keeps both crops in range,
+    and the reference's inverse map recovers the road height from either crop's own sidecar."""
+    from lanemapping_b200.convert_data import multiprocessing_las_files
+    path = str(tmp_path / "000007.las")
+    xyz, inten, _ = _write_road_las(path, 100.0, 200.0, lambda x: 50.0 + 30.0 * (x > 57.6), 300_000, 4, outlier=10.0, gap=57.6)
+    res = {}
+    for mode in ("file", "min", "robust"):
+        tiff, param = str(tmp_path / ("tiff_" + mode)), str(tmp_path / ("param_" + mode))
+        stems = multiprocessing_las_files([path], tiff, param, num_process=1, min_ele=mode)
+        man = json.load(open(os.path.join(param, "000007.manifest.json")))
+        res[mode] = ([sidecar.read_sidecar(os.path.join(param, s + ".txt")).local_min_ele for s in stems],
+                     [man["elevation_saturated_fraction"][s] for s in stems])
+        if mode == "robust":
+            for k, stem in enumerate(stems):
+                p = sidecar.read_sidecar(os.path.join(param, stem + ".txt"))
+                img = np.array(Image.open(os.path.join(tiff, stem + ".png")), dtype=np.uint8)
+                occ = img[..., 2] > 0
+                z_back = img[..., 1][occ].astype(np.float64) * p.ele_reso + p.local_min_ele + p.las_read_offset[2]
+                assert np.abs(np.median(z_back) - (50.0 + 30.0 * k)) < 0.1
+    # local frame: las_read_offset z = floor(10.0) = 10 -> outlier at 0, road at 40 (crop 0) and 70 (crop 1)
+    assert res["file"][0] == [0.0, 0.0] and min(res["file"][1]) > 0.99            # the outlier drags the whole file down
+    assert res["min"][0][0] == 0.0 and abs(res["min"][0][1] - 69.9) < 0.11        # crop 0 still follows its outlier
+    assert res["min"][1][0] > 0.99 and res["min"][1][1] == 0.0
+    assert res["robust"][1] == [0.0, 0.0]
+    assert abs(res["robust"][0][0] - 39.4) < 0.11 and abs(res["robust"][0][1] - 69.4) < 0.11
 
 
 def test_on_the_fly_projector_matches_png_loader_path(bev, tmp_path):

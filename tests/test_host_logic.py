@@ -45,3 +45,27 @@ def test_split_modes(tmp_path):
     assert read_split(str(tmp_path), "s.json", "all") == stems
     with pytest.raises(AssertionError):
         read_split(str(tmp_path), "s.json", "val")                           # reference asserts on unknown modes
+
+
+def test_seq_ids_are_unique_per_run_and_read_offset_comes_from_the_data(tmp_path):
+    from lanemapping_b200.convert_data import assign_seq_ids, data_read_offset, seq_id_of
+    files = ["/d/181013_0131.las", "/d/181013_0130.las", "/d/2021-03-15_run1.las", "/d/2021-03-15_run2.las", "/d/x.las"]
+    assert seq_id_of(files[0]) == 181013 == seq_id_of(files[1])               # the suggestion collides ...
+    ids = assign_seq_ids(files)
+    assert len(set(ids.values())) == len(files)                                # ... the assignment does not
+    assert ids["/d/181013_0130.las"] == 181013 and ids["/d/181013_0131.las"] == 181014
+    assert ids["/d/2021-03-15_run1.las"] == 202103 and ids["/d/2021-03-15_run2.las"] == 202104 and ids["/d/x.las"] == 0
+    assert assign_seq_ids(list(reversed(files))) == ids                        # deterministic in the file list
+    assert data_read_offset((533100.37, 3380200.9, -4.2)) == (533100.0, 3380200.0, -5.0)
+    # header bounds: written by write_las, parsed by read_header; a header without bounds is flagged
+    xyz = np.array([[10.5, 20.25, 3.0], [11.5, 19.0, 4.0], [12.0, 21.0, 2.5]])
+    path = str(tmp_path / "b.las")
+    las.write_las(path, xyz, np.arange(3))
+    raw, hdr = las.read_point_block(path)
+    assert hdr.bounds_ok() and hdr.mins == (10.5, 19.0, 2.5) and hdr.maxs == (12.0, 21.0, 4.0)
+    assert las.world_min(raw, hdr) == (10.5, 19.0, 2.5)
+    blank = bytearray(open(path, "rb").read())
+    blank[179:227] = bytes(48)
+    open(path, "wb").write(bytes(blank))
+    raw2, hdr2 = las.read_point_block(path)
+    assert not hdr2.bounds_ok() and las.world_min(raw2, hdr2) == (10.5, 19.0, 2.5)
