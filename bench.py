@@ -14,8 +14,12 @@ A *step* is one pass of the hot path over one synthetic cloud.
 ``value``  device-resident throughput (inputs in HBM when the clock starts), CUDA events,
            max over ranks.   ``e2e``: the same metric through the host-buffer API
            (pinned H2D of the points + D2H of the finished raster inside the timed region).
-``roofline`` is for the dominant kernel (bin_points), timed live with events between the
-           pipeline stages of the same timed steps.
+``roofline`` is for the dominant kernel, timed live with events between the pipeline stages of the same
+           timed steps: ``sweep_kernel`` (algo auto: the whole path in one kernel) or ``bin_points`` (algo binned).
+``parity_checked`` / ``mismatches``: after the timed region the timed output is compared on the device with the
+           global-atomic cross-check algorithm on the same points, and a 2 M-point sub-scene with the numpy oracle.
+``configs``  (N = 1) the other BASELINE.json configs and the shuffled ordering, each device-resident, best of 3,
+           with its own path fraction and parity flag.
 """
 from __future__ import annotations
 
@@ -107,30 +111,66 @@ def cpu_sample(spec, n_sample, n_total, seed_rank=0):
     return sub, cloud, what
 
 
+def numpy_single_thread(cloud, spec, n=5_000_000):
+    """Mpoints/s of the plain single-thread numpy oracle on the first n points."""
+    from oracle import bev_oracle as O
+    sub = cloud[:n]
+    O.rasterize(sub[:100_000], spec)
+    t0 = time.perf_counter()
+    O.rasterize(sub, spec)
+    return len(sub) / (time.perf_counter() - t0) / 1e6
+
+
+def png_encode_ms(spec):
+    """ms to PNG-encode one 1152^2 crop the way the offline converter does (cv2, compression 1)."""
+    import cv2
+    from lanemapping_b200.synth import make_cloud
+    from oracle import bev_oracle as O
+    from dataclasses import replace
+    sp = replace(spec, height=1152, width=1152, row0=0, col0=0)
+    img = O.rasterize(make_cloud(2_000_000, sp, order="scan"), sp)["image"]
+    cv2.imencode(".png", img, [cv2.IMWRITE_PNG_COMPRESSION, 1])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cv2.imencode(".png", img, [cv2.IMWRITE_PNG_COMPRESSION, 1])
+    return (time.perf_counter() - t0) / 3 * 1e3
+
+
 def run_reference(args):
+    """CPU arm: the numpy oracle (a port -- the reference has no rasteriser) over multiprocessing.Pool(all cores),
+    the reference's own offline idiom (data/convert_data.py:429-436).  Honours --steps / --warmup; every step is
+    one pooled rasterisation of the sample (default: the FULL config, sample_fraction 1.0)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     spec, n_full, name = workload(args.gpus, 0, args.points)
-    n_sample = min(n_full, args.cpu_points)
-    sub, cloud, what = cpu_sample(spec, n_sample, n_full * args.gpus)
+    n_total = n_full * args.gpus
+    n_sample = min(n_total, args.cpu_points if args.cpu_points > 0 else n_total)
+    sub, cloud, what = cpu_sample(spec, n_sample, n_total)
     n_sample = len(cloud)
     P = os.cpu_count() or 1
-    for _ in range(max(0, min(args.warmup, 1))):
+    W, K = max(0, args.warmup), max(1, args.steps)
+    for _ in range(W):
         cpu_rasterize_timed(cloud, sub, P, 1)
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(K):
         cpu_rasterize_timed(cloud, sub, P, 1)
-    dt = (time.perf_counter() - t0) / steps
+    dt = (time.perf_counter() - t0) / K
     v = n_sample / dt / 1e6
     sample = f"{what}; numpy oracle (floor keys, bincount, maximum.at) over multiprocessing.Pool({P}) row strips"
+    cb = {"value": round(v, 3), "unit": UNIT, "cores": P, "kind": "port", "sample": sample,
+          "sample_fraction": round(n_sample / n_total, 4)}
+    try:
+        cb["numpy_1thread_mpoints_per_s"] = round(numpy_single_thread(cloud, sub), 3)
+        cb["png_encode_ms_per_1152_crop"] = round(png_encode_ms(spec), 2)
+    except Exception as ex:      # the extras must never cost the line
+        cb["extras_error"] = repr(ex)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": name, "sample": sample},
-        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": P, "kind": "port", "sample": sample},
+        "config": {"workload": name, "sample": sample, "sample_fraction": cb["sample_fraction"]},
+        "cpu_baseline": cb,
         "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -203,6 +243,102 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def _timed_best(fn, stream, reps=3, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    stream.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def _same(a, b):
+    """number of differing elements of two device tensors (0 = bit-identical)"""
+    import torch
+    return int((a != b).sum().item()) if a.shape == b.shape else -1
+
+
+def other_configs(dev, peak, algo, pts_cfg2, spec2, stream):
+    """BASELINE.json configs[0], [3], [4] and the shuffled ordering of configs[1]: device-resident, best of 3, each
+    checked on the device against the global-atomic cross-check algorithm (bit-identical = parity true)."""
+    import torch
+    from lanemapping_b200.bev import BatchRasterizer, BevRasterizer, crop_tiles
+    from lanemapping_b200.synth import config_spec, make_cloud
+    out = []
+
+    def entry(name, n, spec, ms, mism, extra=None):
+        b_alg = float(spec.algorithmic_bytes(n)) if extra is None or "b_alg" not in extra else extra.pop("b_alg")
+        e = {"config": name, "points": n, "ms": round(ms, 4), "mpoints_per_s": round(n / ms / 1e3, 1),
+             "path_algorithmic_bytes": b_alg, "path_frac": round(b_alg / (ms * 1e-3) / 1e9 / peak, 4),
+             "parity": mism == 0, "mismatches": mism}
+        if extra:
+            e.update(extra)
+        out.append(e)
+
+    # ---- configs[1] shuffled (worst-case ordering of the headline cloud; permuted on the device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2021)
+    shuf = pts_cfg2[torch.randperm(pts_cfg2.shape[0], device=dev, generator=g)].contiguous()
+    r = BevRasterizer(spec2, len(shuf), device=dev, algo=algo, outputs=("image",))
+    o = r.alloc_outputs()
+    ms = _timed_best(lambda: r(shuf, out=o), stream)
+    d = BevRasterizer(spec2, len(shuf), device=dev, algo="direct", outputs=("image",))
+    entry("configs[1] shuffled (same 100M points in random order)", len(shuf), spec2, ms, _same(o["image"], d(shuf)["image"]),
+          {"sweep": r.sweep_state()} if algo == "auto" else None)
+    del shuf, r, d, o
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: batch-8 on-the-fly proj (8 crops x 10M points -> f32 [8,3,1152,1152]); crop 0 doubles as configs[0]
+    spec5, n5 = config_spec(5)
+    clouds = [torch.from_numpy(make_cloud(n5, spec5, seed=100 + b, order="scan")).to(dev) for b in range(8)]
+    br = BatchRasterizer(spec5, 8, 8 * n5, device=dev, outputs=("proj",))
+    ob = br.alloc_outputs()
+    ms = _timed_best(lambda: br(clouds, None, out=ob), stream)
+    mism = 0
+    d5 = BevRasterizer(spec5, n5, device=dev, algo="direct", outputs=("proj",))
+    for b in (0, 7):
+        mism += _same(ob["proj"][b], d5(clouds[b])["proj"])
+    entry("configs[4]: batch-8 on-the-fly proj, 8 x 10M points -> f32 [8,3,1152,1152]", 8 * n5, spec5, ms, mism,
+          {"b_alg": float(16 * 8 * n5 + 8 * 3 * 1152 * 1152 * 4)})
+    # ---- configs[0]: one 10M-point tile, intensity channel
+    spec1, n1 = config_spec(1)
+    r1 = BevRasterizer(spec1, n1, device=dev, algo=algo, outputs=("image",))
+    o1 = r1.alloc_outputs()
+    ms = _timed_best(lambda: r1(clouds[0], out=o1), stream)
+    d1 = BevRasterizer(spec1, n1, device=dev, algo="direct", outputs=("image",))
+    entry("configs[0]: one 10M-point tile, 1152x1152, intensity channel", n1, spec1, ms, _same(o1["image"], d1(clouds[0])["image"]),
+          {"sweep": r1.sweep_state()} if algo == "auto" else None)
+    del clouds, br, ob, d5, r1, o1, d1
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: 0.02 m, 4 x u8 + u16 count, plus the 1152^2 crop tiling of the image (75 crops)
+    spec4, n4 = config_spec(4)
+    p4 = torch.from_numpy(make_cloud(n4, spec4, order="scan")).to(dev)
+    r4 = BevRasterizer(spec4, n4, device=dev, algo=algo, outputs=("image", "count16"))
+    o4 = r4.alloc_outputs()
+    crops = {}
+
+    def step4():
+        r4(p4, out=o4)
+        crops["c"] = crop_tiles(o4["image"], 1152)
+    ms = _timed_best(step4, stream)
+    ms_crop = _timed_best(lambda: crop_tiles(o4["image"], 1152), stream)
+    d4 = BevRasterizer(spec4, n4, device=dev, algo="direct", outputs=("image", "count16"))
+    od = d4(p4)
+    mism = _same(o4["image"], od["image"]) + _same(o4["count16"], od["count16"])
+    mism += _same(crops["c"][1], o4["image"][0:1152, 1152:2304])
+    entry("configs[3]: 100M points, 0.02 m, 28800x3456, 4 x u8 + u16 count, + 1152^2 crop tiling (75 crops)", n4, spec4, ms, mism,
+          {"crop_tiles_ms": round(ms_crop, 4)})
+    return out
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,6 +347,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     spec, n_pts, name = workload(args.gpus, rank, args.points)
+    algo = args.algo if args.gpus == 1 else ("binned" if args.algo == "auto" else args.algo)
 
     from lanemapping_b200.synth import make_cloud
     from lanemapping_b200.strips import strip_bounds
@@ -225,14 +362,29 @@ def run_ours(args):
 
     # ---- CPU baseline first (forks workers: do it before CUDA is initialised), rank 0 at N=1 only
     cpu_baseline = None
+    oracle_sub = None
+    if args.gpus == 1 and rank == 0:
+        # a 2 M-point sub-scene for the parity check against the numpy oracle: the first points of the cloud
+        # on the row window they fall in (scan order: the first ~250 rows; any order: the whole raster)
+        from oracle import bev_oracle as O
+        m = min(n_pts, 2_000_000)
+        rows = spec.height if args.order != "scan" else min(spec.height, 128 * (2 + int(m / max(n_pts / spec.height, 1) / 128)))
+        sub_spec = spec.window(0, rows)
+        oracle_sub = (m, sub_spec, O.rasterize(cloud[:m], sub_spec)["image"])
     if args.gpus == 1 and rank == 0 and not args.no_cpu_baseline:
         P = os.cpu_count() or 1
-        n_sample = min(n_pts, args.cpu_points)
+        n_sample = min(n_pts, args.cpu_points if args.cpu_points > 0 else 20_000_000)
         sub, sample_cloud, what = cpu_sample(spec, n_sample, n_pts)
         n_sample = len(sample_cloud)
         dt = cpu_rasterize_timed(sample_cloud, sub, P, 2)
         cpu_baseline = {"value": round(n_sample / dt / 1e6, 3), "unit": UNIT, "cores": P, "kind": "port",
-                        "sample": f"{what}, numpy oracle over multiprocessing.Pool({P}) row strips, best of 2"}
+                        "sample": f"{what}, numpy oracle over multiprocessing.Pool({P}) row strips, best of 2",
+                        "sample_fraction": round(n_sample / n_pts, 4)}
+        try:
+            cpu_baseline["numpy_1thread_mpoints_per_s"] = round(numpy_single_thread(sample_cloud, sub), 3)
+            cpu_baseline["png_encode_ms_per_1152_crop"] = round(png_encode_ms(spec), 2)
+        except Exception as ex:
+            cpu_baseline["extras_error"] = repr(ex)
         try:      # for scale: the plain-C restatement of the same spec, one scalar loop on one core
             from oracle import c_oracle as CO
             m = min(len(sample_cloud), 10_000_000)
@@ -266,32 +418,28 @@ def run_ours(args):
     sampler = ClockSampler(local_rank).start()
 
     stage_ms = None
+    stage_names = None
     if args.gpus == 1:
-        r = BevRasterizer(spec, n_pts, device=dev, algo=args.algo, outputs=("image",))
+        r = BevRasterizer(spec, n_pts, device=dev, algo=algo, outputs=("image",))
         out = r.alloc_outputs()
         step = lambda: r(pts, out=out)
-        # the same step, split at the stage boundaries with events between (identical work)
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+        # the same step, split at the stage boundaries with events between (identical launches)
+        if algo == "auto":
+            splits = [_cabi.STAGE_SWEEP, _cabi.STAGE_BIN | _cabi.STAGE_INDEX | _cabi.STAGE_REDUCE]
+            stage_names = ["sweep_kernel(+memset, epilogue)", "fall-back kernels (return at once after a good sweep)"]
+            launches_per_step = 6      # sweep, epilogue, 4 gated two-pass kernels (+1 memset node)
+        else:
+            splits = [_cabi.STAGE_BIN, _cabi.STAGE_INDEX, _cabi.STAGE_REDUCE]
+            stage_names = ["bin_points(+memset)", "scan+index", "reduce_tiles"]
+            launches_per_step = 4      # bin_points, scan_tiles, index_chunks, reduce_tiles (+1 memset node)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(splits) + 1)] for _ in range(K)]
 
         def staged(i):
             e = evs[i]
             e[0].record(stream)
-            r(pts, out=out, stages=_cabi.STAGE_BIN)
-            e[1].record(stream)
-            r(pts, out=out, stages=_cabi.STAGE_INDEX)
-            e[2].record(stream)
-            r(pts, out=out, stages=_cabi.STAGE_REDUCE)
-            e[3].record(stream)
-        launches_per_step = 4      # bin_points, scan_tiles, index_chunks, reduce_tiles (+1 memset node)
-        if args.overlap:
-            # EXPERIMENTAL throughput mode: bin_points of scene k+1 under reduce_tiles of
-            # scene k.  The grids must leave room for each other on an SM; the staged pass below (same
-            # kernels, sequential) only feeds the roofline entry and runs after the timed region.
-            os.environ.setdefault("LM_BEV_BIN_CTAS_PER_SM", "2")
-            os.environ.setdefault("LM_BEV_RED_CTAS_PER_SM", "1")
-            from lanemapping_b200.bev import PipelinedRasterizer
-            pr = PipelinedRasterizer(spec, n_pts, device=dev, outputs=("image",))
-            step = lambda: pr.submit(pts)
+            for j, sp in enumerate(splits):
+                r(pts, out=out, stages=sp)
+                e[j + 1].record(stream)
     else:
         from lanemapping_b200.strips import StripRasterizer
         sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev, align=STRIP_ALIGN,
@@ -310,36 +458,46 @@ def run_ours(args):
     barrier()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
-    overlap = args.gpus == 1 and args.overlap
     for i in range(K):
-        if staged is not None and not overlap:
+        if staged is not None:
             staged(i)
         else:
             step()
     if args.gpus > 1:
         sr.flush()
-    if overlap:
-        pr.flush()
     t_stop.record(stream)
     barrier()
     ms_total = t_start.elapsed_time(t_stop)
-    if overlap:
-        pr.check_device_errors()
-        for i in range(K):
-            staged(i)
-        torch.cuda.synchronize()
     if staged is not None:
-        stage_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)])) for j in range(3)]
+        stage_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)])) for j in range(len(splits))]
+    sweep_state = None
     if args.gpus == 1:
         r.check_device_errors()
         n_valid = r.stats()["n_valid"]
+        sweep_state = r.sweep_state() if algo == "auto" else None
     else:
         sr.raster.check_device_errors()
         n_valid = sr.raster.stats()["n_valid"]
 
+    # ---- verify what was timed (N = 1): the timed output against the global-atomic algorithm on the same points,
+    #      and a 2 M-point sub-scene through the same algo against the numpy oracle
+    parity = None
+    if args.gpus == 1:
+        d = BevRasterizer(spec, n_pts, device=dev, algo="direct", outputs=("image",))
+        mism = _same(out["image"], d(pts)["image"])
+        del d
+        m, sub_spec, want = oracle_sub
+        rs = BevRasterizer(sub_spec, m, device=dev, algo=algo, outputs=("image",))
+        mism_oracle = int((rs(pts[:m])["image"].cpu().numpy() != want).sum())
+        parity = {"parity_checked": True, "mismatches": mism + mism_oracle,
+                  "parity_how": f"timed raster == LM_ALGO_DIRECT raster of the same {n_pts} points on the device ({mism} differing bytes); "
+                                f"first {m} points on rows [0,{sub_spec.height}) == numpy oracle ({mism_oracle} differing bytes)"}
+        del rs
+        torch.cuda.empty_cache()
+
     # ---- e2e through the host-buffer API: pinned H2D + kernels (+ collectives) + D2H
     if args.gpus == 1:
-        hr = HostRasterizer(spec, n_pts, device=dev, algo=args.algo, outputs=("image",))
+        hr = HostRasterizer(spec, n_pts, device=dev, algo=algo, outputs=("image",))
         e2e_step = lambda: hr(host_pts)
         d2h = spec.cells * spec.n_channels
     else:
@@ -363,6 +521,9 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    if args.gpus == 1:
+        del hr
+        torch.cuda.empty_cache()
 
     # ---- max over ranks
     if world > 1:
@@ -380,45 +541,54 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": name, "order": args.order, "algo": args.algo,
-                       **({"pipeline": "experimental: bin_points(k+1) on one stream under index+reduce_tiles(k) on another; "
-                                       "stage_ms from a sequential pass after the timed region"} if args.gpus == 1 and args.overlap else {}),
+            "config": {"workload": name, "order": args.order, "algo": algo,
                        **({"mosaic": "gathered on rank 0" if args.gather == "root" else "all-gathered on every rank"} if args.gpus > 1 else {}),
                        "points_per_gpu": n_pts, "valid_points_rank0": int(n_valid),
-                       "l2_policy": "inputs (1.6+ GB of points per step) exceed the 126 MB L2; no flush needed",
+                       "l2_policy": "inputs (1.6+ GB of points per step) exceed the 126 MB L2; no flush needed; the 39.8 MB "
+                                    "output image is rewritten every step and partly stays in L2 (2.4 % of the algorithmic bytes)",
                        "timing": "CUDA events on the launch stream, barrier+synchronize both sides, max over ranks"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_pts * 16,
                     "d2h_bytes_per_step": int(d2h), "steps": Ke},
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
         }
+        if parity is not None:
+            line.update(parity)
+        if sweep_state is not None:
+            line["config"]["sweep"] = sweep_state
         if stage_ms is not None:
-            # dominant kernel = bin_points: every point record (16 B) read exactly once
-            b_alg_kernel = 16.0 * n_pts
-            achieved = b_alg_kernel / (stage_ms[0] * 1e-3) / 1e9
             b_alg_path = float(spec.algorithmic_bytes(n_pts))
+            # dominant kernel: the sweep does the whole path (every point read once, every cell written once);
+            # bin_points of the two-pass pipeline reads every point record (16 B) once
+            kernel = "sweep_kernel" if algo == "auto" else "bin_points_kernel"
+            b_alg_kernel = b_alg_path if algo == "auto" else 16.0 * n_pts
+            achieved = b_alg_kernel / (stage_ms[0] * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
                 try:
                     with open(tp) as f:
-                        traffic = json.load(f).get("bin_points_dram_bytes_per_launch_100M")
-                    if n_pts != 100_000_000:
+                        traffic = json.load(f).get(kernel.replace("_kernel", "") + "_dram_bytes_per_launch_100M")
+                    if n_pts != 100_000_000 or args.order != "scan":
                         traffic = None
                 except Exception:
                     traffic = None
             line["roofline"] = {
-                "bound": "hbm", "kernel": "bin_points_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_alg_kernel,
-                "stage_ms": {"bin_points(+memset)": round(stage_ms[0], 4), "scan+index": round(stage_ms[1], 4),
-                             "reduce_tiles": round(stage_ms[2], 4)},
+                "stage_ms": {nm: round(v, 4) for nm, v in zip(stage_names, stage_ms)},
                 "path_algorithmic_bytes": b_alg_path,
                 "path_achieved": round(b_alg_path / (ms_step * 1e-3) / 1e9, 1),
                 "path_frac": round(b_alg_path / (ms_step * 1e-3) / 1e9 / peak, 4),
             }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if args.gpus == 1 and args.configs == "all" and args.points == 0 and args.order == "scan":
+            try:
+                line["configs"] = other_configs(dev, peak, algo, pts, spec, stream)
+            except Exception as ex:      # never lose the headline line over the extras
+                line["configs_error"] = repr(ex)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -432,16 +602,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--order", default="scan", choices=["scan", "shuffled"])
-    ap.add_argument("--algo", default="binned", choices=["binned", "direct"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "binned", "direct"],
+                    help="auto: single-pass sweep with the two-pass kernels as fall-back (N = 1); binned: two-pass only")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="N = 1: also measure the other BASELINE configs + the shuffled ordering (adds ~2 min)")
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (debug)")
     ap.add_argument("--halo", type=int, default=64)
     ap.add_argument("--gather", default="root", choices=["root", "all"],
                     help="N > 1: assemble the mosaic on rank 0 (gather) or on every rank (all-gather)")
-    ap.add_argument("--cpu-points", type=int, default=20_000_000, help="bounded sample for the CPU arm")
+    ap.add_argument("--cpu-points", type=int, default=0,
+                    help="points of the CPU sample (0: the full config for --impl reference, 20 M for the in-line cpu_baseline)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N = 1, experimental: pipeline consecutive scenes (bin_points of k+1 under reduce_tiles of k)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

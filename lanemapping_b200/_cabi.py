@@ -8,9 +8,9 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
-ALGO_BINNED, ALGO_DIRECT = 0, 1
-STAGE_BIN, STAGE_INDEX, STAGE_REDUCE, STAGE_ALL = 1, 2, 4, 7
+ABI_VERSION = 3
+ALGO_BINNED, ALGO_DIRECT, ALGO_AUTO = 0, 1, 2
+STAGE_BIN, STAGE_INDEX, STAGE_REDUCE, STAGE_SWEEP, STAGE_ALL = 1, 2, 4, 8, 15
 DEV_ERR_POOL, DEV_ERR_CELL_OVERFLOW = 1, 2
 
 
@@ -87,6 +87,9 @@ SYMBOLS = {
     "lm_bev_last_error": (C.c_char_p, []),
     "lm_bev_workspace_bytes": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(LmBevOutputs),
                                          C.POINTER(C.c_size_t)]),
+    "lm_bev_workspace_init": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(LmBevOutputs), C.c_void_p,
+                                        C.c_size_t, C.c_void_p]),
+    "lm_bev_sweep_state_offset": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t)]),
     "lm_bev_rasterize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
                                    C.POINTER(LmBevOutputs), C.c_void_p]),
     "lm_bev_rasterize_stages": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,

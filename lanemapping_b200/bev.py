@@ -14,7 +14,9 @@ import torch
 from . import _cabi
 from .spec import ACC_PLANES, BevSpec
 
-ALGOS = {"binned": _cabi.ALGO_BINNED, "direct": _cabi.ALGO_DIRECT}
+# "auto": the single-pass sweep where the raster and the cloud allow it, the binned kernels behind it as the
+# exact fall-back (include/lm_bev.h LM_ALGO_AUTO); "binned": the two-pass pipeline alone; "direct": cross-check
+ALGOS = {"binned": _cabi.ALGO_BINNED, "direct": _cabi.ALGO_DIRECT, "auto": _cabi.ALGO_AUTO}
 OUTPUT_KEYS = ("image", "count16", "proj", "acc")
 
 
@@ -68,6 +70,35 @@ class BevRasterizer:
         self._lib = _cabi.lib()
         self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo, outputs, self.acc_band),
                                      dtype=torch.uint8, device=self.device)
+        if algo == "auto":
+            # the sweep's mailboxes keep state between calls: prepare them once (include/lm_bev.h)
+            o = self._sizing_outputs()
+            with torch.cuda.device(self.device):
+                _cabi.check(self._lib.lm_bev_workspace_init(C.byref(self._params), self.max_points, ALGOS[algo], C.byref(o),
+                                                            self.workspace.data_ptr(), self.workspace.numel(),
+                                                            torch.cuda.current_stream(self.device).cuda_stream))
+
+    def _sizing_outputs(self) -> "_cabi.LmBevOutputs":
+        o = _cabi.LmBevOutputs()
+        for k in self.outputs:                      # only non-NULL-ness (and the band) matters for the layout
+            setattr(o, k + "_dev", 1)
+        o.acc_band = self.acc_band
+        return o
+
+    def sweep_state(self) -> dict:
+        """``algo='auto'`` diagnostics (synchronises): calls done by the sweep / fallen back on this workspace."""
+        if self.algo != "auto":
+            return {}
+        off = C.c_size_t(0)
+        _cabi.check(self._lib.lm_bev_sweep_state_offset(self.workspace.numel(), C.byref(off)))
+        v = self.workspace[off.value:off.value + 16].cpu().numpy().view(np.uint32)
+        return {"cooldown": int(v[1]), "n_failed": int(v[2]), "n_ok": int(v[3])}
+
+    def sweep_debug(self) -> list:
+        """Event counters of a -DLM_SWEEP_DEBUG build (zeros otherwise); see csrc/lm_sweep.cuh SW_DBG."""
+        off = C.c_size_t(0)
+        _cabi.check(self._lib.lm_bev_sweep_state_offset(self.workspace.numel(), C.byref(off)))
+        return [int(x) for x in self.workspace[off.value + 16:off.value + 16 + 96].cpu().numpy().view(np.uint64)]
 
     # -- buffers ----------------------------------------------------------------------------
     def alloc_outputs(self) -> Dict[str, torch.Tensor]:

@@ -117,7 +117,9 @@ struct KParams {
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
     unsigned int reserved0;
     unsigned int tile_counter;  // reduce_tiles scheduler
-    unsigned int pad[6];
+    unsigned int sweep_fail;    // LM_ALGO_AUTO: != 0 -> the two-pass kernels behind the sweep do the raster
+    unsigned int next_batch;    // sweep: batch counter of the producers
+    unsigned int pad[4];
 };
 
 struct Ws {                  // device pointers into the caller's workspace
@@ -135,7 +137,10 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t pool_chunks;    // P
     uint32_t region;         // chunks per bin CTA: CTA b owns chunk ids [b * region, (b + 1) * region), local id 0 = none
     uint32_t bin_grid;       // bin CTAs of this launch
+    const unsigned int *gate = nullptr;   // non-NULL: the kernels of the two-pass path return at once unless *gate != 0
+                                // (they sit behind a sweep, lm_sweep.cuh, and only run when it gave up)
 };
+__device__ __forceinline__ bool gated_off(const Ws &ws) { return ws.gate != nullptr && *ws.gate == 0u; }
 
 struct Outs {
     uint8_t *image;
@@ -619,6 +624,7 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
 
 __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kernel(KParams kp, const float4 *__restrict__ pts,
                                                                                long long n, Ws ws) {
+    if (gated_off(ws)) return;
     bin_points_body<false, false>(kp, pts, n, ws, nullptr, nullptr);
 }
 __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_batch_kernel(KParams kp, const __grid_constant__ BatchTab bt,
@@ -689,6 +695,7 @@ __device__ __forceinline__ bool tile_in_band(const KParams &kp, int t) {
 }
 
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
+    if (gated_off(ws)) return;
     const int T = kp.T;
     __shared__ uint32_t s_part[1024];
     __shared__ uint32_t s_lvl[1024];
@@ -736,6 +743,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
 }
 
 __global__ void index_chunks_kernel(Ws ws) {
+    if (gated_off(ws)) return;
     if (ws.stats->error & LM_DEV_ERR_POOL) return;
     // chunk ids are (bin CTA, local id) pairs: CTA b used local ids 1 .. cta_chunks[b] of its region
     const uint32_t total = ws.bin_grid * ws.region;
@@ -878,6 +886,7 @@ __device__ __forceinline__ uint32_t stream_tile(const Ws &ws, const uint32_t *my
 
 template <int MASK>
 __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel(KParams kp, Ws ws, Outs out) {
+    if (gated_off(ws)) return;
     constexpr int NW = popc6(MASK);
     extern __shared__ __align__(16) uint32_t acc[];      // [NW][cells]; plane 0/1 reused as packed/count16
     __shared__ int s_tile;
@@ -1102,6 +1111,8 @@ __global__ void selftest_div_kernel(float c, float rc, unsigned long long *out) 
     }
 }
 
+#include "lm_sweep.cuh"
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1250,6 +1261,14 @@ struct Layout {
     uint32_t pool_chunks;
     int bin_ctas;
 };
+constexpr size_t SW_HEADS_WORDS = (size_t)SW_PRODUCERS * SW_OWNERS;
+constexpr size_t SW_MAIL_WORDS = SW_HEADS_WORDS * SW_CAP * 8;
+// The sweep's state survives from call to call, so it must not move when a call brings fewer points than the
+// workspace was sized for (the two-pass layout depends on n_points): it occupies the last SW_REGION_BYTES of the
+// workspace, [persistent block | consumer heads | mailboxes], each 256-byte aligned.
+constexpr size_t SW_OFF_HEADS = 256, SW_OFF_MAIL = SW_OFF_HEADS + (SW_HEADS_WORDS * 4 + 255) / 256 * 256;
+constexpr size_t SW_REGION_BYTES = SW_OFF_MAIL + (SW_MAIL_WORDS * 4 + 255) / 256 * 256 + 256;
+size_t sweep_region(size_t workspace_bytes) { return (workspace_bytes - SW_REGION_BYTES + 255) / 256 * 256; }
 
 int bin_ctas_for(long long n) {
     const long long nb = (n + BIN_BATCH - 1) / BIN_BATCH;
@@ -1288,8 +1307,60 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
     L->off_index = o; o = align_up(o + (size_t)chunks * HALVES * 4, 256);
     L->off_pool = o;  o = align_up(o + (size_t)chunks * CHUNK_RECS * 4, 256);
+    if (algo == LM_ALGO_AUTO) o += SW_REGION_BYTES;     // the sweep's state: the LAST bytes of the workspace (sweep_region)
     L->total = o;
     return LM_OK;
+}
+
+// the sweep handles: one launch window, image / count16 / proj outputs, channels out of {max_i, mean_z, density},
+// rasters up to SW_MAX_LG * 4 * 148 columns, and needs all its CTAs resident at once
+bool sweep_mask_ok(int mask) { return mask == M_MAXI || mask == (M_CNT | M_MAXI) || mask == (M_CNT | M_SUMZ | M_MAXI); }
+bool sweep_eligible(const lm_bev_params *p, const lm_bev_outputs *out, int mask, int n_win, bool las) {
+    if (las || n_win != 1 || out->acc_dev) return false;
+    if (!sweep_mask_ok(mask)) return false;
+    for (int c = 0; c < p->n_channels; ++c)
+        if (p->channels[c] != LM_CH_MAX_I && p->channels[c] != LM_CH_MEAN_Z && p->channels[c] != LM_CH_DENSITY) return false;
+    if ((p->width + 3) / 4 > SW_MAX_LG * SW_OWNERS) return false;
+    return true;
+}
+uint32_t sweep_magic(const void *w, size_t total) {
+    return 0x5EEB0001u ^ (uint32_t)(reinterpret_cast<uintptr_t>(w) >> 8) ^ (uint32_t)total * 2654435761u;
+}
+SweepWs make_sweep_ws(unsigned char *w, size_t workspace_bytes, Ctl *ctl) {
+    unsigned char *r = w + sweep_region(workspace_bytes);
+    SweepWs sw;
+    sw.persist = reinterpret_cast<SweepPersist *>(r);
+    sw.heads = reinterpret_cast<uint32_t *>(r + SW_OFF_HEADS);
+    sw.mail = reinterpret_cast<uint4 *>(r + SW_OFF_MAIL);
+    sw.fail = &ctl->sweep_fail;
+    sw.next_batch = &ctl->next_batch;
+    sw.stats = reinterpret_cast<lm_bev_stats *>(w);
+    sw.magic = sweep_magic(w, workspace_bytes);
+    return sw;
+}
+// fits = every CTA of the sweep can be resident at once (producers and consumers wait for each other);
+// launch = false only asks that question
+template <int MASK>
+cudaError_t launch_sweep(const KParams &kp, const float4 *pts, long long n, const SweepWs &sw, const Outs &o, int sms, bool *fits,
+                         bool launch, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(sweep_kernel<MASK>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<MASK>, SW_THREADS, SW_SMEM);
+    if (e != cudaSuccess) return e;
+    *fits = (long long)occ * sms >= SW_GRID;
+    if (!*fits || !launch) return cudaSuccess;
+    sweep_kernel<MASK><<<SW_GRID, SW_THREADS, SW_SMEM, st>>>(kp, pts, n, sw, o);
+    return cudaGetLastError();
+}
+cudaError_t launch_sweep_mask(int mask, const KParams &kp, const float4 *pts, long long n, const SweepWs &sw, const Outs &o, int sms,
+                              bool *fits, bool launch, cudaStream_t st) {
+    switch (mask) {
+        case M_MAXI: return launch_sweep<M_MAXI>(kp, pts, n, sw, o, sms, fits, launch, st);
+        case M_CNT | M_MAXI: return launch_sweep<M_CNT | M_MAXI>(kp, pts, n, sw, o, sms, fits, launch, st);
+        default: return launch_sweep<M_CNT | M_SUMZ | M_MAXI>(kp, pts, n, sw, o, sms, fits, launch, st);
+    }
 }
 
 // Grid and chunk region of one bin launch (the same values in every stage-split call of a raster):
@@ -1374,7 +1445,7 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
     int rc = validate(p);
     if (rc) return rc;
     if (!bytes || n_points < 0) return fail(LM_ERR_INVALID, "bytes is NULL or n_points < 0");
-    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
+    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_AUTO) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
     // the tile height depends on the accumulator planes the outputs need; without an output set
     // size for the smallest tiles (raw accumulators) so that any call fits
     int th = 5;
@@ -1385,7 +1456,7 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
         th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16), p->height, p->width);
     }
     KParams k = make_kparams(p, th);
-    if (algo == LM_ALGO_BINNED) {          // a raster with too many tiles runs as row windows: size for one window
+    if (algo != LM_ALGO_DIRECT) {          // a raster with too many tiles runs as row windows: size for one window
         const int wrows = window_rows(p, th);
         if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: %d tiles per tile row > %d", k.tiles_x, max_tiles());
         lm_bev_params pw = *p;
@@ -1396,6 +1467,28 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
     rc = make_layout(p, n_points, algo, k.T, &L);
     if (rc) return rc;
     *bytes = L.total;
+    return LM_OK;
+}
+
+int lm_bev_workspace_init(const lm_bev_params *p, int64_t n_points, int algo, const lm_bev_outputs *out,
+                          void *workspace_dev, size_t workspace_bytes, void *stream) {
+    size_t need = 0;
+    int rc = lm_bev_workspace_bytes(p, n_points, algo, out, &need);
+    if (rc) return rc;
+    if (!workspace_dev || (reinterpret_cast<uintptr_t>(workspace_dev) & 255))
+        return fail(LM_ERR_WORKSPACE, "workspace_dev is NULL or not 256-byte aligned");
+    if (workspace_bytes < need) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+    if (algo != LM_ALGO_AUTO) return LM_OK;
+    unsigned char *w = static_cast<unsigned char *>(workspace_dev);
+    const SweepWs sw = make_sweep_ws(w, workspace_bytes, reinterpret_cast<Ctl *>(w + align_up(sizeof(lm_bev_stats), 64)));
+    sweep_init_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sw, SW_HEADS_WORDS, SW_MAIL_WORDS);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "workspace_init launch");
+}
+
+int lm_bev_sweep_state_offset(size_t workspace_bytes, size_t *offset) {
+    if (!offset || workspace_bytes < SW_REGION_BYTES + 4096) return fail(LM_ERR_INVALID, "not an LM_ALGO_AUTO workspace size");
+    *offset = sweep_region(workspace_bytes);
     return LM_OK;
 }
 
@@ -1428,7 +1521,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
         return fail(LM_ERR_INVALID, "no output buffer requested");
     if (!workspace_dev || (reinterpret_cast<uintptr_t>(workspace_dev) & 255))
         return fail(LM_ERR_WORKSPACE, "workspace_dev is NULL or not 256-byte aligned");
-    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
+    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_AUTO) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char *w = static_cast<unsigned char *>(workspace_dev);
     const Outs o = {out->image_dev, out->count16_dev, out->proj_dev, out->acc_dev, out->acc_band};
@@ -1493,6 +1586,16 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
     ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
     ws.acc = nullptr;
     ws.pool_chunks = L.pool_chunks;
+    ws.gate = nullptr;
+    bool sweep = algo == LM_ALGO_AUTO && sweep_eligible(p, out, mask, n_win, las != nullptr);
+    SweepWs sw;
+    if (sweep) {
+        sw = make_sweep_ws(w, workspace_bytes, ws.ctl);
+        cudaError_t e = launch_sweep_mask(mask, make_kparams(&pw, th), nullptr, 0, sw, o, sms, &sweep, false, st);
+        if (e != cudaSuccess) return cuda_fail(e, "sweep occupancy");
+    }
+    // behind a sweep the two-pass kernels return at once unless ctl->sweep_fail says that it gave up (or was skipped)
+    if (sweep) ws.gate = &ws.ctl->sweep_fail;
 
     for (int win = 0; win < n_win; ++win) {
         // the window is an integer sub-window of the same global grid: bit-identical to the one-piece raster
@@ -1514,11 +1617,21 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
             rc = bin_geometry(las ? (const void *)bin_points_las_kernel : (const void *)bin_points_kernel, smem, nb, kp.T, kp.tiles_x, sms, L, &ws, &grid);
             if (rc) return rc;
         }
-        if (stages & LM_STAGE_BIN) {
-            // stats (first 64 bytes) accumulate over the windows; everything else restarts
-            const size_t skip = win == 0 && !keep_stats ? 0 : L.off_ctl;
-            e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
+        if (sweep && (stages & LM_STAGE_SWEEP)) {
+            e = cudaMemsetAsync(w, 0, L.zero_bytes, st);
             if (e != cudaSuccess) return cuda_fail(e, "memset");
+            bool fits = true;
+            e = launch_sweep_mask(mask, kp, reinterpret_cast<const float4 *>(points_dev), n_points, sw, o, sms, &fits, true, st);
+            if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
+            sweep_epilogue_kernel<<<1, 1, 0, st>>>(sw);
+        }
+        if (stages & LM_STAGE_BIN) {
+            if (!sweep) {      // (the sweep stage has zeroed the tables already, and left its verdict in them)
+                // stats (first 64 bytes) accumulate over the windows; everything else restarts
+                const size_t skip = win == 0 && !keep_stats ? 0 : L.off_ctl;
+                e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
+                if (e != cudaSuccess) return cuda_fail(e, "memset");
+            }
             if (n_points > 0 && las)
                 bin_points_las_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, *las, reinterpret_cast<const unsigned char *>(points_dev), n_points, ws);
             else if (n_points > 0)
