@@ -15,7 +15,7 @@ A *step* is one pass of the hot path over one synthetic cloud.
            max over ranks.   ``e2e``: the same metric through the host-buffer API
            (pinned H2D of the points + D2H of the finished raster inside the timed region).
 ``roofline`` is for the dominant kernel, timed live with events between the pipeline stages of the same
-           timed steps: ``sweep_kernel`` (algo auto: the whole path in one kernel) or ``bin_points`` (algo binned).
+           timed steps: ``sweep_kernel`` (algo sweep: the whole path in one kernel) or ``bin_points`` (algo binned).
 ``parity_checked`` / ``mismatches``: after the timed region the timed output is compared on the device with the
            global-atomic cross-check algorithm on the same points, and a 2 M-point sub-scene with the numpy oracle.
 ``configs``  (N = 1) the other BASELINE.json configs and the shuffled ordering, each device-resident, best of 3,
@@ -282,6 +282,17 @@ def other_configs(dev, peak, algo, pts_cfg2, spec2, stream):
             e.update(extra)
         out.append(e)
 
+    # ---- configs[1] through the experimental single-pass sweep (no record pool in HBM), same cloud
+    if algo != "sweep":
+        rs = BevRasterizer(spec2, len(pts_cfg2), device=dev, algo="sweep", outputs=("image",))
+        os_ = rs.alloc_outputs()
+        ms = _timed_best(lambda: rs(pts_cfg2, out=os_), stream)
+        dd = BevRasterizer(spec2, len(pts_cfg2), device=dev, algo="direct", outputs=("image",))
+        entry("configs[1] scan order through LM_ALGO_SWEEP (experimental single-pass kernel)", len(pts_cfg2), spec2, ms,
+              _same(os_["image"], dd(pts_cfg2)["image"]), {"sweep": rs.sweep_state()})
+        del rs, os_, dd
+        torch.cuda.empty_cache()
+
     # ---- configs[1] shuffled (worst-case ordering of the headline cloud; permuted on the device)
     g = torch.Generator(device=dev)
     g.manual_seed(2021)
@@ -291,7 +302,7 @@ def other_configs(dev, peak, algo, pts_cfg2, spec2, stream):
     ms = _timed_best(lambda: r(shuf, out=o), stream)
     d = BevRasterizer(spec2, len(shuf), device=dev, algo="direct", outputs=("image",))
     entry("configs[1] shuffled (same 100M points in random order)", len(shuf), spec2, ms, _same(o["image"], d(shuf)["image"]),
-          {"sweep": r.sweep_state()} if algo == "auto" else None)
+          {"sweep": r.sweep_state()} if algo == "sweep" else None)
     del shuf, r, d, o
     torch.cuda.empty_cache()
 
@@ -314,7 +325,7 @@ def other_configs(dev, peak, algo, pts_cfg2, spec2, stream):
     ms = _timed_best(lambda: r1(clouds[0], out=o1), stream)
     d1 = BevRasterizer(spec1, n1, device=dev, algo="direct", outputs=("image",))
     entry("configs[0]: one 10M-point tile, 1152x1152, intensity channel", n1, spec1, ms, _same(o1["image"], d1(clouds[0])["image"]),
-          {"sweep": r1.sweep_state()} if algo == "auto" else None)
+          {"sweep": r1.sweep_state()} if algo == "sweep" else None)
     del clouds, br, ob, d5, r1, o1, d1
     torch.cuda.empty_cache()
 
@@ -347,7 +358,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     spec, n_pts, name = workload(args.gpus, rank, args.points)
-    algo = args.algo if args.gpus == 1 else ("binned" if args.algo == "auto" else args.algo)
+    algo = args.algo if args.gpus == 1 else ("binned" if args.algo == "sweep" else args.algo)
 
     from lanemapping_b200.synth import make_cloud
     from lanemapping_b200.strips import strip_bounds
@@ -424,7 +435,7 @@ def run_ours(args):
         out = r.alloc_outputs()
         step = lambda: r(pts, out=out)
         # the same step, split at the stage boundaries with events between (identical launches)
-        if algo == "auto":
+        if algo == "sweep":
             splits = [_cabi.STAGE_SWEEP, _cabi.STAGE_BIN | _cabi.STAGE_INDEX | _cabi.STAGE_REDUCE]
             stage_names = ["sweep_kernel(+memset, epilogue)", "fall-back kernels (return at once after a good sweep)"]
             launches_per_step = 6      # sweep, epilogue, 4 gated two-pass kernels (+1 memset node)
@@ -474,7 +485,7 @@ def run_ours(args):
     if args.gpus == 1:
         r.check_device_errors()
         n_valid = r.stats()["n_valid"]
-        sweep_state = r.sweep_state() if algo == "auto" else None
+        sweep_state = r.sweep_state() if algo == "sweep" else None
     else:
         sr.raster.check_device_errors()
         n_valid = sr.raster.stats()["n_valid"]
@@ -560,8 +571,8 @@ def run_ours(args):
             b_alg_path = float(spec.algorithmic_bytes(n_pts))
             # dominant kernel: the sweep does the whole path (every point read once, every cell written once);
             # bin_points of the two-pass pipeline reads every point record (16 B) once
-            kernel = "sweep_kernel" if algo == "auto" else "bin_points_kernel"
-            b_alg_kernel = b_alg_path if algo == "auto" else 16.0 * n_pts
+            kernel = "sweep_kernel" if algo == "sweep" else "bin_points_kernel"
+            b_alg_kernel = b_alg_path if algo == "sweep" else 16.0 * n_pts
             achieved = b_alg_kernel / (stage_ms[0] * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -602,8 +613,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--order", default="scan", choices=["scan", "shuffled"])
-    ap.add_argument("--algo", default="auto", choices=["auto", "binned", "direct"],
-                    help="auto: single-pass sweep with the two-pass kernels as fall-back (N = 1); binned: two-pass only")
+    ap.add_argument("--algo", default="binned", choices=["binned", "sweep", "direct"],
+                    help="binned: the two-pass product path; sweep: experimental single-pass kernel with the two-pass kernels "
+                         "as fall-back (N = 1); direct: global atomics (cross-check)")
     ap.add_argument("--configs", default="all", choices=["all", "none"],
                     help="N = 1: also measure the other BASELINE configs + the shuffled ordering (adds ~2 min)")
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (debug)")

@@ -56,11 +56,12 @@ enum {
 enum {
     LM_ALGO_BINNED = 0, /* product path: bin -> index -> per-tile shared-memory reduce  */
     LM_ALGO_DIRECT = 1, /* global-atomic accumulate + finalize; cross-check path        */
-    LM_ALGO_AUTO   = 2  /* single-pass sweep (records routed through L2-resident mailboxes to  */
-                        /* column-owner CTAs, no record pool in HBM) where the raster and the   */
-                        /* cloud allow it, with the BINNED kernels queued behind it as the      */
-                        /* exact fall-back (they return at once unless the sweep gave up).      */
-                        /* Needs lm_bev_workspace_init once per workspace.  Same results.       */
+    LM_ALGO_SWEEP  = 2  /* EXPERIMENTAL single-pass sweep: records are routed through L2-resident        */
+                        /* mailboxes to column-owner CTAs (no record pool in HBM: DRAM traffic = 1.0 x   */
+                        /* algorithmic bytes), with the BINNED kernels queued behind it as the exact     */
+                        /* fall-back (they return at once unless the sweep gave up).  Same results on    */
+                        /* every input; slower than BINNED today (instruction-bound).  Needs  */
+                        /* lm_bev_workspace_init once per workspace.                                     */
 };
 
 enum {
@@ -133,13 +134,13 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo,
                            const lm_bev_outputs *out, size_t *bytes);
 
 /* Prepare a freshly allocated workspace (sized by lm_bev_workspace_bytes with the SAME p, n_points, algo,
- * out) for LM_ALGO_AUTO: the sweep's mailboxes keep state between calls.  Enqueues one kernel; call it
+ * out) for LM_ALGO_SWEEP: the sweep's mailboxes keep state between calls.  Enqueues one kernel; call it
  * once per workspace (again after the workspace memory was used for something else).  A workspace that
  * was never initialised is detected and simply always takes the fall-back.  No-op for other algos.  */
 int lm_bev_workspace_init(const lm_bev_params *p, int64_t n_points, int algo, const lm_bev_outputs *out,
                           void *workspace_dev, size_t workspace_bytes, void *stream);
 
-/* Byte offset, inside an LM_ALGO_AUTO workspace of workspace_bytes bytes, of four uint32 {magic, cooldown, n_failed, n_ok}: how many
+/* Byte offset, inside an LM_ALGO_SWEEP workspace of workspace_bytes bytes, of four uint32 {magic, cooldown, n_failed, n_ok}: how many
  * calls on this workspace were done by the sweep (n_ok) and how many fell back (n_failed); cooldown > 0 =
  * the sweep is switched off for that many further calls after a failure.  Diagnostics only.          */
 int lm_bev_sweep_state_offset(size_t workspace_bytes, size_t *offset);
@@ -155,7 +156,7 @@ int lm_bev_rasterize(const lm_bev_params *p, const float *points_dev, int64_t n_
 /* Same call, restricted to some pipeline stages (for per-kernel timing with events between
  * the stages; running BIN, INDEX, REDUCE back to back on one stream == lm_bev_rasterize).
  * LM_ALGO_DIRECT: BIN = init + accumulate, REDUCE = finalize, INDEX = nothing.            */
-/* LM_ALGO_AUTO: SWEEP = the single-pass kernel (it zeroes the tables and leaves its verdict there, so a stage-split
+/* LM_ALGO_SWEEP: SWEEP = the single-pass kernel (it zeroes the tables and leaves its verdict there, so a stage-split
  * sequence starts with it); BIN, INDEX, REDUCE = the fall-back kernels behind it.                          */
 enum { LM_STAGE_BIN = 1, LM_STAGE_INDEX = 2, LM_STAGE_REDUCE = 4, LM_STAGE_SWEEP = 8, LM_STAGE_ALL = 15 };
 int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,

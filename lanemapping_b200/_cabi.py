@@ -9,7 +9,7 @@ import os
 from .build import LIB_PATH
 
 ABI_VERSION = 3
-ALGO_BINNED, ALGO_DIRECT, ALGO_AUTO = 0, 1, 2
+ALGO_BINNED, ALGO_DIRECT, ALGO_SWEEP = 0, 1, 2
 STAGE_BIN, STAGE_INDEX, STAGE_REDUCE, STAGE_SWEEP, STAGE_ALL = 1, 2, 4, 8, 15
 DEV_ERR_POOL, DEV_ERR_CELL_OVERFLOW = 1, 2
 

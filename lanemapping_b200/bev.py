@@ -14,9 +14,11 @@ import torch
 from . import _cabi
 from .spec import ACC_PLANES, BevSpec
 
-# "auto": the single-pass sweep where the raster and the cloud allow it, the binned kernels behind it as the
-# exact fall-back (include/lm_bev.h LM_ALGO_AUTO); "binned": the two-pass pipeline alone; "direct": cross-check
-ALGOS = {"binned": _cabi.ALGO_BINNED, "direct": _cabi.ALGO_DIRECT, "auto": _cabi.ALGO_AUTO}
+# "binned": the two-pass pipeline (the product path); "direct": global atomics, cross-check; "sweep": EXPERIMENTAL
+# single-pass kernel (no record pool in HBM) with the binned kernels queued behind it as the exact fall-back
+# (include/lm_bev.h LM_ALGO_SWEEP) -- correct on every input, HBM traffic 1.0 x algorithmic, but slower than
+# "binned" today (profiles/README.md)
+ALGOS = {"binned": _cabi.ALGO_BINNED, "direct": _cabi.ALGO_DIRECT, "sweep": _cabi.ALGO_SWEEP}
 OUTPUT_KEYS = ("image", "count16", "proj", "acc")
 
 
@@ -70,7 +72,7 @@ class BevRasterizer:
         self._lib = _cabi.lib()
         self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo, outputs, self.acc_band),
                                      dtype=torch.uint8, device=self.device)
-        if algo == "auto":
+        if algo == "sweep":
             # the sweep's mailboxes keep state between calls: prepare them once (include/lm_bev.h)
             o = self._sizing_outputs()
             with torch.cuda.device(self.device):
@@ -86,8 +88,8 @@ class BevRasterizer:
         return o
 
     def sweep_state(self) -> dict:
-        """``algo='auto'`` diagnostics (synchronises): calls done by the sweep / fallen back on this workspace."""
-        if self.algo != "auto":
+        """``algo="sweep"`` diagnostics (synchronises): calls done by the sweep / fallen back on this workspace."""
+        if self.algo != "sweep":
             return {}
         off = C.c_size_t(0)
         _cabi.check(self._lib.lm_bev_sweep_state_offset(self.workspace.numel(), C.byref(off)))

@@ -117,7 +117,7 @@ struct KParams {
 struct Ctl {                 // lives right after lm_bev_stats in the workspace; zeroed per call
     unsigned int reserved0;
     unsigned int tile_counter;  // reduce_tiles scheduler
-    unsigned int sweep_fail;    // LM_ALGO_AUTO: != 0 -> the two-pass kernels behind the sweep do the raster
+    unsigned int sweep_fail;    // LM_ALGO_SWEEP: != 0 -> the two-pass kernels behind the sweep do the raster
     unsigned int next_batch;    // sweep: batch counter of the producers
     unsigned int pad[4];
 };
@@ -1307,7 +1307,7 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_meta = o;  o = align_up(o + (size_t)chunks * sizeof(uint2), 256);
     L->off_index = o; o = align_up(o + (size_t)chunks * HALVES * 4, 256);
     L->off_pool = o;  o = align_up(o + (size_t)chunks * CHUNK_RECS * 4, 256);
-    if (algo == LM_ALGO_AUTO) o += SW_REGION_BYTES;     // the sweep's state: the LAST bytes of the workspace (sweep_region)
+    if (algo == LM_ALGO_SWEEP) o += SW_REGION_BYTES;     // the sweep's state: the LAST bytes of the workspace (sweep_region)
     L->total = o;
     return LM_OK;
 }
@@ -1445,7 +1445,7 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
     int rc = validate(p);
     if (rc) return rc;
     if (!bytes || n_points < 0) return fail(LM_ERR_INVALID, "bytes is NULL or n_points < 0");
-    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_AUTO) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
+    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_SWEEP) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
     // the tile height depends on the accumulator planes the outputs need; without an output set
     // size for the smallest tiles (raw accumulators) so that any call fits
     int th = 5;
@@ -1478,7 +1478,7 @@ int lm_bev_workspace_init(const lm_bev_params *p, int64_t n_points, int algo, co
     if (!workspace_dev || (reinterpret_cast<uintptr_t>(workspace_dev) & 255))
         return fail(LM_ERR_WORKSPACE, "workspace_dev is NULL or not 256-byte aligned");
     if (workspace_bytes < need) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
-    if (algo != LM_ALGO_AUTO) return LM_OK;
+    if (algo != LM_ALGO_SWEEP) return LM_OK;
     unsigned char *w = static_cast<unsigned char *>(workspace_dev);
     const SweepWs sw = make_sweep_ws(w, workspace_bytes, reinterpret_cast<Ctl *>(w + align_up(sizeof(lm_bev_stats), 64)));
     sweep_init_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sw, SW_HEADS_WORDS, SW_MAIL_WORDS);
@@ -1487,7 +1487,7 @@ int lm_bev_workspace_init(const lm_bev_params *p, int64_t n_points, int algo, co
 }
 
 int lm_bev_sweep_state_offset(size_t workspace_bytes, size_t *offset) {
-    if (!offset || workspace_bytes < SW_REGION_BYTES + 4096) return fail(LM_ERR_INVALID, "not an LM_ALGO_AUTO workspace size");
+    if (!offset || workspace_bytes < SW_REGION_BYTES + 4096) return fail(LM_ERR_INVALID, "not an LM_ALGO_SWEEP workspace size");
     *offset = sweep_region(workspace_bytes);
     return LM_OK;
 }
@@ -1521,7 +1521,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
         return fail(LM_ERR_INVALID, "no output buffer requested");
     if (!workspace_dev || (reinterpret_cast<uintptr_t>(workspace_dev) & 255))
         return fail(LM_ERR_WORKSPACE, "workspace_dev is NULL or not 256-byte aligned");
-    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_AUTO) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
+    if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_SWEEP) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char *w = static_cast<unsigned char *>(workspace_dev);
     const Outs o = {out->image_dev, out->count16_dev, out->proj_dev, out->acc_dev, out->acc_band};
@@ -1587,7 +1587,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
     ws.acc = nullptr;
     ws.pool_chunks = L.pool_chunks;
     ws.gate = nullptr;
-    bool sweep = algo == LM_ALGO_AUTO && sweep_eligible(p, out, mask, n_win, las != nullptr);
+    bool sweep = algo == LM_ALGO_SWEEP && sweep_eligible(p, out, mask, n_win, las != nullptr);
     SweepWs sw;
     if (sweep) {
         sw = make_sweep_ws(w, workspace_bytes, ws.ctl);

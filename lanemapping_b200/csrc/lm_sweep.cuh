@@ -1,4 +1,4 @@
-// lm_sweep.cuh -- LM_ALGO_AUTO's single-pass path: one persistent kernel, no record pool in HBM.
+// lm_sweep.cuh -- LM_ALGO_SWEEP's single-pass path: one persistent kernel, no record pool in HBM.
 // Included by lm_bev.cu inside its anonymous namespace (uses KParams, Outs, the per-point quantisation,
 // mean_small, store_pixels4 and the lm_dev.cuh helpers).
 //
@@ -33,7 +33,9 @@
 #pragma once
 
 constexpr int SW_OWNERS = 148;                     // consumer CTAs = cell owners (one per B200 SM)
-constexpr int SW_PRODUCERS = 3 * SW_OWNERS;        // producer CTAs
+constexpr int SW_PRODUCERS = 2 * SW_OWNERS;        // producer CTAs
+constexpr int SW_CTAS_PER_SM = 3;                  // 1 consumer + 2 producers: 3 x 70 KB of shared memory
+constexpr int SW_STAGES = 3;                       // TMA stage buffers of a producer
 constexpr int SW_GRID = SW_OWNERS + SW_PRODUCERS;
 constexpr int SW_THREADS = 256;
 constexpr int SW_PPT = 4;
@@ -41,11 +43,13 @@ constexpr int SW_BATCH = SW_THREADS * SW_PPT;      // points per producer batch
 constexpr int SW_RS = 32;                          // slots of a per-owner ring in producer shared memory
 constexpr int SW_CAP_LOG2 = 3;
 constexpr int SW_CAP = 1 << SW_CAP_LOG2;           // granules per (producer, owner) mailbox ring
-constexpr int SW_R_LOG2 = 9;
+constexpr int SW_R_LOG2 = 10;
 constexpr int SW_R = 1 << SW_R_LOG2;               // rows of the consumer's sliding window
 constexpr int SW_M = 16;                           // rows kept open below the frontier
 constexpr int SW_ADV = 96;                         // a producer renews its marker when its batches moved this far
-constexpr int SW_SMAX = 256;                       // records stay below marker + SW_SMAX
+constexpr int SW_SMAX = 512;                       // records stay below marker + SW_SMAX
+constexpr int SW_TAG_BITS = 11;                    // a record carries row mod 2^11: with base <= row < marker + SW_SMAX <= base + 2^11
+constexpr int SW_TAG_SPAN = 1 << SW_TAG_BITS;      //   (the marker gate) the consumer recovers row - base exactly
 constexpr int SW_STRIDE = 41;                      // ownership rotation per row block (coprime with 148)
 constexpr int SW_RB_LOG2 = 3;                      // rows per ownership block
 constexpr int SW_MAX_LG = 2;                       // 4-column groups per owner and row (W <= 4 * 148 * 2)
@@ -54,9 +58,11 @@ constexpr int SW_MBPT = (SW_PRODUCERS + SW_THREADS - 1) / SW_THREADS;   // mailb
 constexpr uint32_t SW_PHASE = 1u << 31, SW_VALID = 1u << 30, SW_MARKER = 1u << 29, SW_DONE = 1u << 28;
 constexpr int SW_INF_ROW = 0x7fffffff;
 constexpr int SW_COOLDOWN = 16;                    // calls a failed sweep stays off on its workspace
+constexpr int SW_FRONTIER_EVERY = 1;               // consumer loops between two frontier updates
 constexpr int SW_PAD_ROUND = 64;                   // retry rounds (~20 us) after which a waiting producer pads its rings out
 static_assert(SW_RS % 8 == 0 && SW_RS >= 16, "ring = whole granules");
-static_assert(SW_SMAX + SW_M + 8 <= SW_R, "the gate must leave room for the lowest marker");
+static_assert(SW_SMAX + SW_M + 8 <= SW_TAG_SPAN && SW_R <= SW_TAG_SPAN, "the gate must leave room for the lowest marker");
+static_assert(SW_MAX_LG * 4 <= 8, "3 bits of owner-local column");
 
 struct SweepPersist {            // survives between calls (lm_bev_workspace_init writes it)
     uint32_t magic;
@@ -79,21 +85,25 @@ struct SweepWs {
     uint32_t magic;
 };
 
-constexpr size_t SW_PROD_SMEM = 2 * (size_t)SW_BATCH * 16 + (size_t)SW_OWNERS * SW_RS * 4 + 3 * (size_t)SW_OWNERS * 4;
+constexpr size_t SW_PROD_SMEM = SW_STAGES * (size_t)SW_BATCH * 16 + (size_t)SW_OWNERS * SW_RS * 4 + 3 * (size_t)SW_OWNERS * 4;
 constexpr size_t SW_CONS_SMEM = 2 * (size_t)SW_R * SW_CPO * 4;
 constexpr size_t SW_SMEM = SW_PROD_SMEM > SW_CONS_SMEM ? SW_PROD_SMEM : SW_CONS_SMEM;
 
+// Mailbox words, heads and the fail flag are read at the L2 (ld.global.cg: never from a stale L1 line) with WEAK
+// loads: the protocol needs no ordering between them (phase bits / monotonic counters), and strong (volatile)
+// accesses of one thread are performed one after the other -- four L2 round trips in series per consumer loop
+// (measured: 7.4 us per loop with ld.volatile).
 __device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t *p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_vol_u32(uint32_t *p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.global.cg.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ld_vol_u4(const uint4 *p) {
     uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
@@ -109,6 +119,13 @@ __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) {
 }
 __device__ __forceinline__ void reds_max(uint32_t a, uint32_t v) {
     asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// predicated forms: ONE instruction under a predicate, never a branch around it
+__device__ __forceinline__ void reds_add_if(bool p, uint32_t a, uint32_t v) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q red.shared.add.u32 [%1], %2;\n}" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void reds_max_if(bool p, uint32_t a, uint32_t v) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q red.shared.max.u32 [%1], %2;\n}" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long sweep_now_ns() {
@@ -146,11 +163,11 @@ __device__ __forceinline__ void sweep_producer(const KParams &kp, const float4 *
                                                const uint32_t pid, unsigned char *smem_raw, uint64_t *s_bar, int *s_misc) {
     const int tid = threadIdx.x;
     const uint32_t sm_stage = smem_u32(smem_raw);
-    const uint32_t sm_ring = sm_stage + 2u * SW_BATCH * 16u;
+    const uint32_t sm_ring = sm_stage + (uint32_t)SW_STAGES * SW_BATCH * 16u;
     const uint32_t sm_pos = sm_ring + (uint32_t)SW_OWNERS * SW_RS * 4u;     // records appended per owner (absolute)
     const uint32_t sm_flushed = sm_pos + (uint32_t)SW_OWNERS * 4u;          // records flushed per owner (multiple of 8)
     const uint32_t sm_headc = sm_flushed + (uint32_t)SW_OWNERS * 4u;        // cached consumer head (granules)
-    // s_misc: [0],[1] claimed batches (double buffer), [2] batch min row, [3] batch max row, [4] abort
+    // s_misc: [2] batch min row, [3] batch max row, [4] abort, [5 .. 5+SW_STAGES) claimed batches (ring)
     const long long nb = (n + SW_BATCH - 1) / SW_BATCH;
     uint32_t *my_heads = sw.heads + (size_t)pid * SW_OWNERS;
     uint4 *my_mail = sw.mail + (size_t)pid * SW_OWNERS * SW_CAP * 2;
@@ -161,18 +178,23 @@ __device__ __forceinline__ void sweep_producer(const KParams &kp, const float4 *
         sts_u32(sm_flushed + 4u * tid, h << 3);
         sts_u32(sm_headc + 4u * tid, h);
     }
+    auto claim_and_load = [&](int slot, bool abort) {           // thread 0: next batch of the stream -> stage `slot`
+        const long long b = abort ? nb : (long long)atomicAdd(sw.next_batch, 1u);
+        s_misc[5 + slot] = b < nb ? (int)b : -1;
+        if (b < nb) {
+            const long long left = n - b * SW_BATCH;
+            bulk_load_stream(smem_raw + (uint32_t)slot * (SW_BATCH * 16u), pts + b * SW_BATCH,
+                             (uint32_t)(left < SW_BATCH ? left : SW_BATCH) * 16u, &s_bar[slot]);
+        }
+    };
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+#pragma unroll
+        for (int b = 0; b < SW_STAGES; ++b) mbar_init(&s_bar[b], 1);
         s_misc[2] = SW_INF_ROW;
         s_misc[3] = -1;
         s_misc[4] = 0;
-        const long long b = (long long)atomicAdd(sw.next_batch, 1u);
-        s_misc[0] = b < nb ? (int)b : -1;
-        if (b < nb) {
-            const long long left = n - b * SW_BATCH;
-            bulk_load_stream(smem_raw, pts + b * SW_BATCH, (uint32_t)(left < SW_BATCH ? left : SW_BATCH) * 16u, &s_bar[0]);
-        }
+#pragma unroll
+        for (int b = 0; b < SW_STAGES - 1; ++b) claim_and_load(b, false);     // SW_STAGES - 1 batches fly ahead
     }
     __syncthreads();
 
@@ -223,26 +245,18 @@ __device__ __forceinline__ void sweep_producer(const KParams &kp, const float4 *
     bool have_marker = false, panic = false;
     unsigned long long d_rounds = 0, d_markers = 0, d_batches = 0, d_wait = 0, d_tma = 0;
     for (int k = 0;; ++k) {
-        const int cur = s_misc[k & 1];
+        const uint32_t buf = (uint32_t)k % (uint32_t)SW_STAGES;
+        const int cur = s_misc[5 + buf];
         if (cur < 0) break;                                  // block-uniform
-        const uint32_t buf = (uint32_t)k & 1u;
-        if (tid == 0) {
-            // claim the next batch and start its copy into the buffer consumed one batch ago
-            const bool abort = s_misc[4] != 0 || ld_vol_u32((const uint32_t *)sw.fail) != 0u;
-            long long b = abort ? nb : (long long)atomicAdd(sw.next_batch, 1u);
-            s_misc[(k + 1) & 1] = b < nb ? (int)b : -1;
-            if (b < nb) {
-                const long long left = n - b * SW_BATCH;
-                bulk_load_stream(smem_raw + (buf ^ 1u) * (SW_BATCH * 16u), pts + b * SW_BATCH,
-                                 (uint32_t)(left < SW_BATCH ? left : SW_BATCH) * 16u, &s_bar[buf ^ 1u]);
-            }
-        }
+        if (tid == 0)   // claim one more batch and start its copy into the buffer consumed one batch ago
+            claim_and_load((int)((uint32_t)(k + SW_STAGES - 1) % (uint32_t)SW_STAGES),
+                           s_misc[4] != 0 || ld_vol_u32((const uint32_t *)sw.fail) != 0u);
         const long long left = n - (long long)cur * SW_BATCH;
         const uint32_t npts = left < SW_BATCH ? (uint32_t)left : (uint32_t)SW_BATCH;
 #ifdef LM_SWEEP_DEBUG
         const unsigned long long t_w0 = sweep_now_ns();
 #endif
-        mbar_wait(&s_bar[buf], ((uint32_t)k >> 1) & 1u);
+        mbar_wait(&s_bar[buf], ((uint32_t)k / (uint32_t)SW_STAGES) & 1u);
 #ifdef LM_SWEEP_DEBUG
         d_tma += sweep_now_ns() - t_w0;
         ++d_batches;
@@ -335,7 +349,7 @@ __device__ __forceinline__ void sweep_producer(const KParams &kp, const float4 *
             if (ok[j] && !skip) {
                 uint32_t lcol;
                 sweep_owner(r[j], c[j], own[j], lcol);
-                word[j] = SW_VALID | (lcol << 26) | (((uint32_t)r[j] & 1023u) << 16) | (iq[j] << 8) | zq[j];
+                word[j] = SW_VALID | (lcol << 27) | (((uint32_t)r[j] & (SW_TAG_SPAN - 1)) << 16) | (iq[j] << 8) | zq[j];
                 ps[j] = atoms_add(sm_pos + 4u * own[j], 1u);
                 pend |= 1u << j;
             }
@@ -363,8 +377,8 @@ __device__ __forceinline__ void sweep_producer(const KParams &kp, const float4 *
 #ifdef LM_SWEEP_DEBUG
             const unsigned long long t_s0 = sweep_now_ns();
 #endif
-            if (round > 2) {
-                __nanosleep(200);
+            {
+                __nanosleep(round < 4 ? 300 : 1000);
                 if ((round & 255) == 0 && __syncthreads_or(sweep_panic(sw, t_start))) { panic = true; break; }
             }
 #ifdef LM_SWEEP_DEBUG
@@ -526,51 +540,56 @@ __device__ __forceinline__ void sweep_consumer(const KParams &kp, const SweepWs 
             if (done[i]) continue;
             const uint32_t p = (uint32_t)tid + (uint32_t)i * SW_THREADS;
             const uint4 *mb = sw.mail + ((size_t)p * SW_OWNERS + oid) * SW_CAP * 2;
+            const uint4 lo = glo[i], hi = ghi[i];
+            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            const uint32_t exp = ((head[i] >> SW_CAP_LOG2) & 1u) << 31;
+            uint32_t diff = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) diff |= (w[q] ^ exp);
+            ++d_polls;
+            // Words are taken in order; a record that does not fit the window under the promise in force stops the
+            // granule there (resumed at `sub` in a later loop).  Markers in front of it are applied, so the mailbox
+            // with the lowest promise always moves on.  Straight-line code: every lane of the warp has its own
+            // granule with its own mix of records, markers and pads, so everything is selects and predicated
+            // atomics (a branchy version ran 60 instructions per word: ncu, profiles/r02_sweep_v2).
+            const bool ready = !(diff & SW_PHASE);                    // all 8 words have arrived
             {
-                const uint4 lo = glo[i], hi = ghi[i];
-                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                const uint32_t exp = ((head[i] >> SW_CAP_LOG2) & 1u) << 31;
-                uint32_t diff = 0;
+                bool stop = !ready;
+                uint32_t nsub = sub[i], taken = 0;
+                int cm = mark[i];
+                bool bad = false, fin = false;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) diff |= (w[q] ^ exp);
-                ++d_polls;
-                if (!(diff & SW_PHASE)) {                             // all 8 words of the granule have arrived
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t x = w[q];
+                    const bool act = !stop && (uint32_t)q >= sub[i];
+                    const bool is_mk = act && (x & (SW_VALID | SW_MARKER)) == SW_MARKER;
+                    const bool is_fin = is_mk && (x & SW_DONE) != 0u;
+                    const int v = (int)(x & 0xFFFFFFu);
+                    bad |= is_mk && !is_fin && v < base;               // rows that were already emitted: the cloud is not row-ordered
+                    cm = is_fin ? SW_INF_ROW : (is_mk ? v : cm);
+                    fin |= is_fin;
+                    saw |= is_mk;
+                    const bool rec = act && (x & SW_VALID) != 0u;
+                    // row - base from the 11-bit tag: exact while the promise in force keeps the row below
+                    // base + 2^11 (first test); the record waits for the frontier while it is beyond the window
+                    const uint32_t ahead = ((x >> 16) - (uint32_t)base) & (SW_TAG_SPAN - 1);
+                    const bool held = rec && (cm + SW_SMAX > base + SW_TAG_SPAN || ahead >= (uint32_t)SW_R);
+                    nsub = held ? (uint32_t)q : nsub;
+                    stop |= held;
+                    const bool take = rec && !held;
+                    taken += take ? 1u : 0u;
+                    const uint32_t slot = ((((x >> 16) & (SW_R - 1)) * SW_CPO) + ((x >> 27) & 7u)) * 4u;   // always inside the window
+                    const uint32_t iqv = (x >> 8) & 0xFFu;
+                    if (HAS_CNT) reds_add_if(take, sm_w0 + slot, (1u << PK_SHIFT) | (HAS_SUM ? (x & 0xFFu) : 0u));
+                    reds_max_if(take && iqv > lds_u32(sm_w1 + slot), sm_w1 + slot, iqv);
+                }
+                n_valid += taken;
+                mark[i] = cm;
+                if (ready) {
                     ++d_hits;
-                    bool go = true;
-                    uint32_t nsub = 8;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (go && (uint32_t)q >= sub[i]) {
-                            const uint32_t x = w[q];
-                            if (x & SW_VALID) {
-                                if (mark[i] + SW_SMAX > base + SW_R) {    // too far ahead of the window: wait for the frontier
-                                    go = false;
-                                    nsub = q;
-                                } else {
-                                    const uint32_t slot = ((((x >> 16) & (SW_R - 1)) * SW_CPO) + ((x >> 26) & 15u)) * 4u;
-                                    const uint32_t iqv = (x >> 8) & 0xFFu;
-                                    if (HAS_CNT) reds_add(sm_w0 + slot, (1u << PK_SHIFT) | (HAS_SUM ? (x & 0xFFu) : 0u));
-                                    if (iqv > lds_u32(sm_w1 + slot)) reds_max(sm_w1 + slot, iqv);
-                                    ++n_valid;
-                                }
-                            } else if (x & SW_MARKER) {
-                                if (x & SW_DONE) {
-                                    done[i] = true;
-                                    mark[i] = SW_INF_ROW;
-                                    ++n_done_local;
-                                } else {
-                                    const int v = (int)(x & 0xFFFFFFu);
-                                    if (v < base) {                         // rows that were already emitted: the cloud is not row-ordered
-                                        s_misc[10] = 1;
-                                        atomicExch(sw.fail, 1u);            // producers stop claiming batches
-                                    }
-                                    mark[i] = v;
-                                }
-                                saw = true;
-                            }
-                        }
-                    }
-                    if (!go) { sub[i] = nsub; ++d_gated; }
+                    if (bad) { s_misc[10] = 1; atomicExch(sw.fail, 1u); }      // producers stop claiming batches
+                    if (fin) { done[i] = true; ++n_done_local; }
+                    if (stop) { sub[i] = nsub; ++d_gated; }
                     else { sub[i] = 0; ++head[i]; }
                 }
             }
@@ -584,22 +603,24 @@ __device__ __forceinline__ void sweep_consumer(const KParams &kp, const SweepWs 
                 hpub[i] = head[i];
             }
         }
-        // ---- frontier = min over the mailboxes' latest markers; emit the rows that fell below it
-        if (saw) s_misc[12 + (it & 1)] = 1;
+        // ---- every SW_FRONTIER_EVERY loops: frontier = min over the mailboxes' latest markers; emit the rows below it
+        if (saw) s_misc[12] = 1;
         if (n_done_local != done_reported) { atomicAdd(&s_misc[8], n_done_local - done_reported); done_reported = n_done_local; }
+        if ((it % SW_FRONTIER_EVERY) != SW_FRONTIER_EVERY - 1) continue;
         int mn = SW_INF_ROW;
 #pragma unroll
         for (int i = 0; i < SW_MBPT; ++i) mn = min(mn, mark[i]);
         mn = __reduce_min_sync(0xffffffffu, mn);
         if (lane == 0) s_misc[warp] = mn;
         __syncthreads();
-        const bool any_marker = s_misc[12 + (it & 1)] != 0;
+        const bool any_marker = s_misc[12] != 0;
         const bool all_done = s_misc[8] >= SW_THREADS * SW_MBPT;
         int F = SW_INF_ROW;
 #pragma unroll
         for (int q = 0; q < SW_THREADS / 32; ++q) F = min(F, s_misc[q]);
-        if (tid == 0) s_misc[12 + ((it + 1) & 1)] = 0;                 // the next loop's flag: nobody sets it before the barrier
         __syncthreads();
+        if (tid == 0) s_misc[12] = 0;            // (a flag raised before this store by a thread already in the next loop is
+                                                 //  only lost until the next marker: emission is delayed, never wrong)
         if (any_marker || all_done) {
             int nbase = all_done ? H : min(F - SW_M, H);
             if (nbase > base) {
@@ -649,9 +670,9 @@ __device__ __forceinline__ void sweep_consumer(const KParams &kp, const SweepWs 
 }
 
 template <int MASK>
-__global__ void __launch_bounds__(SW_THREADS, 4) sweep_kernel(KParams kp, const float4 *__restrict__ pts, long long n, SweepWs sw, Outs out) {
+__global__ void __launch_bounds__(SW_THREADS, SW_CTAS_PER_SM) sweep_kernel(KParams kp, const float4 *__restrict__ pts, long long n, SweepWs sw, Outs out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_bar[SW_STAGES];
     __shared__ int s_misc[16];
     __shared__ float s_div255[256];
     // the same decision in every CTA: nothing in the persistent block changes while this kernel runs

@@ -1,7 +1,7 @@
 """LM_ALGO_AUTO: the single-pass sweep (csrc/lm_sweep.cuh) against the oracle, and its fall-back.
 
 The sweep is exact by construction for row-ordered clouds and hands any other cloud to the two-pass kernels
-queued behind it, so ``algo='auto'`` must equal the oracle bit for bit on EVERY input; the persistent counters
+queued behind it, so ``algo="sweep"`` must equal the oracle bit for bit on EVERY input; the persistent counters
 (``sweep_state``) tell which of the two did the work."""
 import numpy as np
 import pytest
@@ -41,7 +41,7 @@ def check(r, cloud, spec, outs=("image",)):
 def test_sweep_is_bit_exact_on_scan_ordered_clouds(bev, h, w, n):
     spec = spec_of(h, w)
     cloud = make_cloud(n, spec, seed=5, order="scan")
-    r = bev.BevRasterizer(spec, n, algo="auto", outputs=("image", "proj"))
+    r = bev.BevRasterizer(spec, n, algo="sweep", outputs=("image", "proj"))
     for rep in range(3):                                        # the mailboxes carry their state from call to call
         check(r, cloud, spec, ("image", "proj"))
     s = r.sweep_state()
@@ -54,7 +54,7 @@ def test_sweep_channel_sets(bev, channels, count16):
     spec = spec_of(1500, 1100, channels=channels, count16=count16)
     cloud = make_cloud(2_000_000, spec, seed=9, order="scan")
     outs = ("image", "count16") if count16 else ("image",)
-    r = bev.BevRasterizer(spec, len(cloud), algo="auto", outputs=outs)
+    r = bev.BevRasterizer(spec, len(cloud), algo="sweep", outputs=outs)
     check(r, cloud, spec, outs)
     assert r.sweep_state()["n_ok"] == 1
 
@@ -63,7 +63,7 @@ def test_unordered_cloud_falls_back_and_stays_exact(bev):
     spec = spec_of(2304, 1152)
     shuffled = make_cloud(2_000_000, spec, seed=6, order="shuffled")
     ordered = make_cloud(2_000_000, spec, seed=7, order="scan")
-    r = bev.BevRasterizer(spec, 2_000_000, algo="auto")
+    r = bev.BevRasterizer(spec, 2_000_000, algo="sweep")
     check(r, shuffled, spec)                                    # sweep gives up -> two-pass kernels
     s = r.sweep_state()
     assert s["n_failed"] == 1 and s["n_ok"] == 0 and s["cooldown"] > 0
@@ -80,17 +80,17 @@ def test_inputs_the_sweep_does_not_take(bev):
     """Channels outside {max_i, mean_z, density}, wide rasters, raw accumulators: plain two-pass, same numbers."""
     spec = spec_of(800, 1152, channels=(CH_MAX_I, CH_MEAN_I, CH_DENSITY))
     cloud = make_cloud(500_000, spec, seed=8, order="scan")
-    r = bev.BevRasterizer(spec, len(cloud), algo="auto")
+    r = bev.BevRasterizer(spec, len(cloud), algo="sweep")
     check(r, cloud, spec)
     assert r.sweep_state()["n_ok"] == 0 and r.sweep_state()["n_failed"] == 0
     wide = spec_of(600, 2400)
     cloud = make_cloud(500_000, wide, seed=8, order="scan")
-    check(bev.BevRasterizer(wide, len(cloud), algo="auto"), cloud, wide)
+    check(bev.BevRasterizer(wide, len(cloud), algo="sweep"), cloud, wide)
 
 
 def test_sweep_edge_cases(bev):
     spec = spec_of(1152, 1152)
-    r = bev.BevRasterizer(spec, 1_000_000, algo="auto")
+    r = bev.BevRasterizer(spec, 1_000_000, algo="sweep")
     # empty cloud: every cell is written (zero)
     out = r.alloc_outputs()
     out["image"].fill_(7)
@@ -108,5 +108,5 @@ def test_sweep_edge_cases(bev):
     check(r, srt, spec)
     assert r.sweep_state()["n_failed"] == 1                     # the 5000-point cell does not fit 12 bits
     # one point
-    r2 = bev.BevRasterizer(spec, 10, algo="auto")
+    r2 = bev.BevRasterizer(spec, 10, algo="sweep")
     check(r2, np.array([[1.0, 2.0, 0.0, 900.0]], dtype=np.float32), spec)

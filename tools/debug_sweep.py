@@ -11,7 +11,7 @@ h, w, n = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (2304, 1152,
 spec = BevSpec(h, w, channels=(CH_MAX_I, CH_MEAN_Z, CH_DENSITY), local_min_ele=default_min_ele(BevSpec(1152, 1152)))
 cloud = make_cloud(n, spec, seed=5, order="scan")
 want = CO.rasterize(cloud, spec)["image"]
-r = BevRasterizer(spec, n, algo="auto")
+r = BevRasterizer(spec, n, algo="sweep")
 pts = torch.from_numpy(cloud).cuda()
 for rep in range(2):
     got = r(pts)["image"].cpu().numpy()
