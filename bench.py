@@ -453,16 +453,16 @@ def run_ours(args):
                 e[j + 1].record(stream)
     else:
         from lanemapping_b200.strips import StripRasterizer
-        sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev, align=STRIP_ALIGN,
-                             gather_root=0 if args.gather == "root" else None)
+        groot = {"root": 0, "all": None, "none": "none"}[args.gather]
+        sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev, align=STRIP_ALIGN, gather_root=groot, time_stages=True)
         mosaic_holder = {}
 
         def step():
-            # scene k's mosaic all-gather (side stream) overlaps scene k+1's rasterisation; every gather
-            # completes inside the timed region (sr.flush() before the closing event)
+            # scene k's halo exchange, merge and mosaic gather (side stream) overlap scene k+1's rasterisation; every
+            # one of them completes inside the timed region (sr.flush() before the closing event)
             mosaic_holder["slot"] = sr.step(pts)
         staged = None
-        launches_per_step = 4 + 2 * 2 + 2     # raster + merge/finalize per neighbour + pack copies (interior rank)
+        launches_per_step = 4 + 2 * (1 if rank in (0, world - 1) else 2)     # raster + one merge_finalize per neighbour (+ NCCL kernels)
 
     for _ in range(Wm):
         step()
@@ -489,6 +489,44 @@ def run_ours(args):
     else:
         sr.raster.check_device_errors()
         n_valid = sr.raster.stats()["n_valid"]
+        stage_t = sr.stage_times()
+        # the same rank's rasterisation alone (no exchange, no gather, no peers' traffic): what the step costs without comm
+        barrier()
+        ro = sr.raster.alloc_outputs()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(K):
+            sr.raster(pts, out=ro)
+        a1.record(stream)
+        a1.synchronize()
+        stage_t["raster_alone"] = a0.elapsed_time(a1) / K
+        del ro
+        # verify what was timed: every rank checks its finished strip of the last timed scene against the independent
+        # DIRECT-algorithm path (strips.verify), rank 0 checks that the gathered mosaic holds the ranks' strips
+        slot = mosaic_holder["slot"]
+        my_strip = sr.strip_of(slot)
+        mism = sr.verify(pts, my_strip)
+        sums = torch.zeros(world, dtype=torch.int64, device=dev)
+        sums[rank] = my_strip.to(torch.int64).sum()
+        dist.all_reduce(sums)
+        mos = sr.mosaic(slot)
+        if mos is not None:
+            rows = [b - a for a, b in sr.plan.bounds]
+            off = 0
+            for k_, rr in enumerate(rows):
+                mism += int(mos[off:off + rr].to(torch.int64).sum().item() != int(sums[k_].item()))
+                off += rr
+            mism += _same(mos[sr.plan.strip[0]:sr.plan.strip[1]], my_strip)
+        mt = torch.tensor([mism], dtype=torch.int64, device=dev)
+        dist.all_reduce(mt)
+        parity_n = {"parity_checked": True, "mismatches": int(mt.item()),
+                    "parity_how": "every rank: finished strip of the last timed scene == LM_ALGO_DIRECT raster of its points with the halo "
+                                  "planes exchanged and merged by torch integer ops; gathered mosaic == the ranks' strips (checksums, own strip bytes)"}
+        st_t = torch.tensor([stage_t.get(k_, 0.0) for k_ in ("raster", "halo_exchange", "merge_finalize", "gather", "side_stream_total", "raster_alone")],
+                            dtype=torch.float64, device=dev)
+        dist.all_reduce(st_t, op=dist.ReduceOp.MAX)
+        stage_n = dict(zip(("raster", "halo_exchange", "merge_finalize", "gather", "side_stream_total", "raster_alone"),
+                           [round(float(v), 4) for v in st_t]))
 
     # ---- verify what was timed (N = 1): the timed output against the global-atomic algorithm on the same points,
     #      and a 2 M-point sub-scene through the same algo against the numpy oracle
@@ -514,15 +552,28 @@ def run_ours(args):
     else:
         dev_in = torch.empty_like(pts)
         r0, r1 = sr.plan.strip
-        host_strip = torch.empty((r1 - r0, spec.width, spec.n_channels), dtype=torch.uint8, pin_memory=True)
+        # what the step pays for is what the e2e delivers: the gathered mosaic goes to the host on the rank that
+        # holds it (rank 0 for --gather root, every rank for all); with --gather none every rank delivers its own strip
+        if args.gather == "none":
+            host_dst = torch.empty((r1 - r0, spec.width, spec.n_channels), dtype=torch.uint8, pin_memory=True)
+        elif args.gather == "all" or rank == 0:
+            host_dst = torch.empty((spec.height, spec.width, spec.n_channels), dtype=torch.uint8, pin_memory=True)
+        else:
+            host_dst = None
 
         def e2e_step():
             dev_in.copy_(host_pts, non_blocking=True)
             slot = sr.step(dev_in)
-            sr.mosaic(slot)                                   # the scene's merge + gather are part of the step
-            host_strip.copy_(sr.strip_of(slot), non_blocking=True)
+            m = sr.mosaic(slot)                                  # the scene's merge + gather are part of the step
+            if args.gather == "none":
+                host_dst.copy_(sr.strip_of(slot), non_blocking=True)
+            elif m is not None:
+                host_dst.copy_(m, non_blocking=True)
             stream.synchronize()
-        d2h = host_strip.numel()
+        d2h = host_dst.numel() if host_dst is not None else 0
+        d2h_t = torch.tensor([d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(d2h_t, op=dist.ReduceOp.MAX)
+        d2h = int(d2h_t.item())
     Ke = max(1, min(K, args.e2e_steps))
     e2e_step()
     barrier()
@@ -553,7 +604,8 @@ def run_ours(args):
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": name, "order": args.order, "algo": algo,
-                       **({"mosaic": "gathered on rank 0" if args.gather == "root" else "all-gathered on every rank"} if args.gpus > 1 else {}),
+                       **({"mosaic": {"root": "gathered on rank 0", "all": "all-gathered on every rank",
+                                      "none": "left sharded (every rank keeps its strip)"}[args.gather]} if args.gpus > 1 else {}),
                        "points_per_gpu": n_pts, "valid_points_rank0": int(n_valid),
                        "l2_policy": "inputs (1.6+ GB of points per step) exceed the 126 MB L2; no flush needed; the 39.8 MB "
                                     "output image is rewritten every step and partly stays in L2 (2.4 % of the algorithmic bytes)",
@@ -565,6 +617,22 @@ def run_ours(args):
         }
         if parity is not None:
             line.update(parity)
+        if args.gpus > 1:
+            line.update(parity_n)
+            b_rank = float(16 * n_pts + (spec.height // world) * spec.width * spec.n_channels)
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "bin_points_kernel (per rank; the strip pipeline is bin + index + reduce + merge_finalize)",
+                "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "stage_ms_max_over_ranks": stage_n,
+                "halo_bytes_sent_per_rank": sr.halo_bytes, "halo_planes": sr.planes, "halo_rows": args.halo,
+                "mosaic_bytes": spec.cells * spec.n_channels,
+                "path_algorithmic_bytes_per_rank": b_rank,
+                "path_achieved": round(b_rank / (ms_step * 1e-3) / 1e9, 1),
+                "path_frac": round(b_rank / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "achieved": round(b_rank / (stage_n["raster_alone"] * 1e-3) / 1e9, 1),
+                "frac": round(b_rank / (stage_n["raster_alone"] * 1e-3) / 1e9 / peak, 4),
+                "note": "achieved/frac: one rank's rasterisation alone (no exchange, no gather); path_*: the whole step incl. "
+                        "halo exchange, merge and mosaic gather on the side stream"}
         if sweep_state is not None:
             line["config"]["sweep"] = sweep_state
         if stage_ms is not None:
@@ -619,9 +687,10 @@ def main():
     ap.add_argument("--configs", default="all", choices=["all", "none"],
                     help="N = 1: also measure the other BASELINE configs + the shuffled ordering (adds ~2 min)")
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (debug)")
-    ap.add_argument("--halo", type=int, default=64)
-    ap.add_argument("--gather", default="root", choices=["root", "all"],
-                    help="N > 1: assemble the mosaic on rank 0 (gather) or on every rank (all-gather)")
+    ap.add_argument("--halo", type=int, default=32,
+                    help="N > 1: halo rows per side (the scan jitter of the synthetic clouds strays <= 20 rows)")
+    ap.add_argument("--gather", default="root", choices=["root", "all", "none"],
+                    help="N > 1: assemble the mosaic on rank 0 (gather), on every rank (all-gather), or leave it sharded")
     ap.add_argument("--cpu-points", type=int, default=0,
                     help="points of the CPU sample (0: the full config for --impl reference, 20 M for the in-line cpu_baseline)")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -201,6 +201,13 @@ int lm_bev_acc_merge(uint32_t *dst_acc_dev, int64_t dst_plane_stride,
 int lm_bev_finalize(const lm_bev_params *p, const uint32_t *acc_dev,
                     int32_t row_begin, int32_t row_end, const lm_bev_outputs *out, void *stream);
 
+/* The two calls above in one launch, for the halo band of a strip: rows [row_begin,row_end) of acc_dev
+ * ([LM_ACC_PLANES][p->height][p->width]) <- merge with the neighbour's planes, then finished into out.
+ * Only the planes whose bit is set in plane_mask (bit k = LM_ACC_* plane k) were sent: recv_dev is
+ * [popcount(plane_mask)][row_end-row_begin][p->width], ascending plane order.                      */
+int lm_bev_merge_finalize(const lm_bev_params *p, uint32_t *acc_dev, int32_t row_begin, int32_t row_end,
+                          const uint32_t *recv_dev, int32_t plane_mask, const lm_bev_outputs *out, void *stream);
+
 /* Cut a [height][width][c] u8 mosaic into non-overlapping tile x tile crops (row-major crop
  * order, ragged edges zero-filled = empty cells): crops_dev is [n_crops][tile][tile][c].
  * tile = 1152 for cropped_tiff (reference configs/Proj_polyline_fpn_vit_vertex_2.py:38).  */

@@ -112,6 +112,8 @@ SYMBOLS = {
     "lm_bev_acc_merge": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "lm_bev_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32,
                                   C.POINTER(LmBevOutputs), C.c_void_p]),
+    "lm_bev_merge_finalize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.POINTER(LmBevOutputs), C.c_void_p]),
     "lm_bev_selftest_div": (C.c_int, [C.c_float, C.c_void_p, C.c_void_p]),
     "lm_bev_selftest_mean": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lm_bev_crop_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -6,7 +6,7 @@ PyTorch is plumbing here: it owns device memory and streams.  All arithmetic run
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Iterable, Optional
+from typing import Dict, Iterable, List, Optional
 
 import numpy as np
 import torch
@@ -409,6 +409,45 @@ def finalize_rows(spec: BevSpec, acc: torch.Tensor, row_begin: int, row_end: int
     with torch.cuda.device(acc.device):
         _cabi.check(_cabi.lib().lm_bev_finalize(C.byref(p), acc.data_ptr(), int(row_begin), int(row_end),
                                                 C.byref(o), st.cuda_stream))
+
+
+def needed_planes(spec: BevSpec) -> List[int]:
+    """The raw accumulator planes (ACC_* ids, ascending) the spec's channels are derived from: the only
+    ones a strip has to send to its neighbour (``merge_finalize_rows``)."""
+    from .spec import (ACC_COUNT, ACC_MAX_I, ACC_MAX_Z, ACC_MIN_Z, ACC_SUM_I, ACC_SUM_Z, CH_DENSITY, CH_MAX_I, CH_MAX_Z,
+                       CH_MEAN_I, CH_MEAN_Z, CH_MIN_Z)
+    need = {CH_MAX_I: (ACC_MAX_I,), CH_MEAN_I: (ACC_COUNT, ACC_SUM_I), CH_MIN_Z: (ACC_MIN_Z,), CH_MAX_Z: (ACC_MAX_Z,),
+            CH_MEAN_Z: (ACC_COUNT, ACC_SUM_Z), CH_DENSITY: (ACC_COUNT,)}
+    s = set()
+    for c in spec.channels:
+        s.update(need[c])
+    if spec.count16:
+        s.add(ACC_COUNT)
+    return sorted(s)
+
+
+def merge_finalize_rows(spec: BevSpec, acc: torch.Tensor, row_begin: int, row_end: int, recv: torch.Tensor,
+                        planes, out: Dict[str, torch.Tensor]) -> None:
+    """Halo band in one launch (``lm_bev_merge_finalize``): rows [row_begin,row_end) of ``acc`` [6,H,W] are merged with
+    the neighbour's planes ``recv`` [len(planes), rows, W] (ascending ACC_* ids in ``planes``) and finished into ``out``."""
+    rows = int(row_end) - int(row_begin)
+    if tuple(acc.shape) != (ACC_PLANES, spec.height, spec.width) or not acc.is_contiguous():
+        raise ValueError("merge_finalize_rows: acc must be contiguous [6,H,W]")
+    planes = list(planes)
+    if planes != sorted(set(planes)) or tuple(recv.shape) != (len(planes), rows, spec.width) or not recv.is_contiguous():
+        raise ValueError("merge_finalize_rows: recv must be contiguous [len(planes), rows, W], planes ascending")
+    mask = 0
+    for pl in planes:
+        mask |= 1 << int(pl)
+    p = _cabi.make_params(spec)
+    o = _cabi.LmBevOutputs()
+    o.image_dev = _ptr(out.get("image"))
+    o.count16_dev = _ptr(out.get("count16"))
+    o.proj_dev = _ptr(out.get("proj"))
+    st = torch.cuda.current_stream(acc.device)
+    with torch.cuda.device(acc.device):
+        _cabi.check(_cabi.lib().lm_bev_merge_finalize(C.byref(p), acc.data_ptr(), int(row_begin), int(row_end),
+                                                      recv.data_ptr(), mask, C.byref(o), st.cuda_stream))
 
 
 def crop_tiles(image: torch.Tensor, tile: int = 1152) -> torch.Tensor:

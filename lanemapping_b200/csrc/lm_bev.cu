@@ -330,6 +330,36 @@ __global__ void acc_merge_kernel(uint32_t *dst, long long dstride, const uint32_
     }
 }
 
+// halo band of a strip: merge the neighbour's raw planes (only those in plane_mask were sent: recv is
+// [popc(mask)][rows][W], ascending plane order) into rows [r0,r1) of the local accumulators and finish the band in
+// the same pass -- one launch instead of merge + finalize
+__global__ void merge_finalize_kernel(KParams kp, uint32_t *acc, int r0, int r1, const uint32_t *__restrict__ recv, int plane_mask, Outs out) {
+    const size_t cells = (size_t)kp.H * kp.W;
+    const size_t n = (size_t)(r1 - r0) * kp.W, base = (size_t)r0 * kp.W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t cell = base + i;
+        uint32_t v[LM_ACC_PLANES];
+        int k = 0;
+#pragma unroll
+        for (int pl = 0; pl < LM_ACC_PLANES; ++pl) {
+            v[pl] = acc[pl * cells + cell];
+            if (plane_mask >> pl & 1) {
+                const uint32_t o = recv[(size_t)k * n + i];
+                ++k;
+                v[pl] = pl <= LM_ACC_SUM_Z ? v[pl] + o : (pl == LM_ACC_MIN_Z ? min(v[pl], o) : max(v[pl], o));
+                acc[pl * cells + cell] = v[pl];
+            }
+        }
+        for (int c = 0; c < kp.nch; ++c) {
+            const uint32_t ch = channel_value(kp.ch[c], v[LM_ACC_COUNT], v[LM_ACC_SUM_I], v[LM_ACC_SUM_Z], v[LM_ACC_MAX_I],
+                                              v[LM_ACC_MIN_Z], v[LM_ACC_MAX_Z]);
+            if (out.image) out.image[cell * kp.nch + c] = (uint8_t)ch;
+            if (out.proj) out.proj[(size_t)c * cells + cell] = __fdiv_rn((float)ch, 255.0f);
+        }
+        if (out.count16) out.count16[cell] = (uint16_t)(v[LM_ACC_COUNT] < 65535u ? v[LM_ACC_COUNT] : 65535u);
+    }
+}
+
 __global__ void crop_tiles_kernel(const uint8_t *__restrict__ img, int H, int W, int C, int tile, int ncx,
                                   uint8_t *__restrict__ crops, size_t total) {
     const size_t row_bytes = (size_t)tile * C;
@@ -1884,6 +1914,21 @@ int lm_bev_finalize(const lm_bev_params *p, const uint32_t *acc_dev, int32_t row
     finalize_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(kp, acc_dev, row_begin, row_end, o);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? LM_OK : cuda_fail(e, "finalize launch");
+}
+
+int lm_bev_merge_finalize(const lm_bev_params *p, uint32_t *acc_dev, int32_t row_begin, int32_t row_end,
+                          const uint32_t *recv_dev, int32_t plane_mask, const lm_bev_outputs *out, void *stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!acc_dev || !out || (plane_mask && !recv_dev)) return fail(LM_ERR_INVALID, "acc_dev/recv_dev/out is NULL");
+    if (plane_mask < 0 || plane_mask >= (1 << LM_ACC_PLANES)) return fail(LM_ERR_INVALID, "plane_mask outside [0, 63]");
+    if (row_begin < 0 || row_end > p->height || row_begin > row_end) return fail(LM_ERR_INVALID, "bad row range");
+    if (row_begin == row_end) return LM_OK;
+    const KParams kp = make_kparams(p, 7);
+    const Outs o = {out->image_dev, out->count16_dev, out->proj_dev, nullptr, 0};
+    merge_finalize_kernel<<<sm_count() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(kp, acc_dev, row_begin, row_end, recv_dev, plane_mask, o);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "merge_finalize launch");
 }
 
 int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, int32_t c, int32_t tile,

@@ -11,8 +11,9 @@ any partition of the points merges exactly.
 * Each rank rasterises the integer window ``[r0-halo, r1+halo)`` of the global grid -- same
   float origin, shifted integer window, so results are bit-identical to the one-piece raster.
 * One exchange step: the raw u32 accumulators of the halo bands go to the neighbours
-  (``batch_isend_irecv`` over NCCL/NVLink), are merged into the neighbour's edge band with
-  ``lm_bev_acc_merge`` and that band is re-finished with ``lm_bev_finalize`` *before*
+  (``batch_isend_irecv`` over NCCL/NVLink) -- only the planes the channel set is derived from, each sent
+  straight from its rows of the accumulator buffer (no pack copy) -- and one kernel
+  (``lm_bev_merge_finalize``) merges them into the neighbour's edge band and re-finishes that band *before*
   quantising to u8.
 * Mosaic gather: the finished strips are gathered on one rank (``gather``, what an offline writer needs)
   or on all of them (``all_gather``) -- 398 MB for config 3.
@@ -66,13 +67,13 @@ class CudaBackend:
         from .bev import BevRasterizer
         return BevRasterizer(spec, max_points, device=self.device, outputs=outputs, acc_band=acc_band)
 
-    def merge(self, dst, src):
-        from .bev import acc_merge_
-        acc_merge_(dst, src)
+    def planes(self, spec: BevSpec):
+        from .bev import needed_planes
+        return needed_planes(spec)
 
-    def finalize(self, spec, acc, r0, r1, out):
-        from .bev import finalize_rows
-        finalize_rows(spec, acc, r0, r1, out)
+    def merge_finalize(self, spec, acc, r0, r1, recv, planes, out):
+        from .bev import merge_finalize_rows
+        merge_finalize_rows(spec, acc, r0, r1, recv, planes, out)
 
 
 @dataclass
@@ -107,12 +108,14 @@ class StripRasterizer:
     """One rank's part of a strip-sharded rasterisation."""
 
     def __init__(self, spec: BevSpec, max_points: int, halo: int = 64, group=None, backend=None,
-                 device: Optional[torch.device | str] = None, align: int = 128, gather_root: Optional[int] = None):
+                 device: Optional[torch.device | str] = None, align: int = 128, gather_root=None,
+                 time_stages: bool = False):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.spec = spec
-        self.gather_root = gather_root          # step(): None = mosaic on every rank, r = on rank r only
+        self.gather_root = gather_root          # step(): None = mosaic on every rank, r = on rank r only, "none" = stays sharded
+        self.time_stages = time_stages          # step(): record events around the stages (stage_times())
         self.plan = make_plan(spec, self.rank, self.world, halo, align)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.backend = backend if backend is not None else CudaBackend(self.device)
@@ -131,12 +134,13 @@ class StripRasterizer:
         self._comm_stream = None
         self._step = 0
         W = spec.width
-        mk = lambda rows: torch.empty((ACC_PLANES, rows, W), dtype=torch.int32, device=self.device)
-        self._send_up = mk(p.top) if p.top else None
+        # only the planes the channels are derived from travel (config 3: count, sum_z, max_i = 3 of 6)
+        self.planes = list(self.backend.planes(spec)) if self.need_acc else []
+        mk = lambda rows: torch.empty((len(self.planes), rows, W), dtype=torch.int32, device=self.device)
         self._recv_up = mk(p.top) if p.top else None
-        self._send_dn = mk(p.bottom) if p.bottom else None
         self._recv_dn = mk(p.bottom) if p.bottom else None
-        self.halo_bytes = sum(t.numel() * 4 for t in (self._send_up, self._send_dn) if t is not None)
+        self.halo_bytes = len(self.planes) * (p.top + p.bottom) * W * 4          # sent per scene by this rank
+        self._stage_events = []                                                   # step(): (raster, exchange, merge, gather) events
 
     # -- one step ---------------------------------------------------------------------------
     def rasterize(self, points: torch.Tensor) -> torch.Tensor:
@@ -149,28 +153,28 @@ class StripRasterizer:
         hl = self.local_spec.height
         return out["image"][p.top:hl - p.bottom]
 
-    def _exchange_and_merge(self, out: Dict[str, torch.Tensor]) -> None:
+    def _exchange_and_merge(self, out: Dict[str, torch.Tensor], events=None) -> None:
         p = self.plan
         acc = out["acc"]
         hl = self.local_spec.height
         ops = []
-        if p.top:       # my top halo rows belong to rank-1; its bottom halo covers my first rows
-            self._send_up.copy_(acc[:, :p.top])
-            ops.append(dist.P2POp(dist.isend, self._send_up, self._peer(self.rank - 1), self.group))
-            ops.append(dist.P2POp(dist.irecv, self._recv_up, self._peer(self.rank - 1), self.group))
-        if p.bottom:
-            self._send_dn.copy_(acc[:, hl - p.bottom:])
-            ops.append(dist.P2POp(dist.isend, self._send_dn, self._peer(self.rank + 1), self.group))
-            ops.append(dist.P2POp(dist.irecv, self._recv_dn, self._peer(self.rank + 1), self.group))
+        for k, pl in enumerate(self.planes):
+            if p.top:       # my top halo rows belong to rank-1; its bottom halo covers my first rows
+                ops.append(dist.P2POp(dist.isend, acc[pl, :p.top], self._peer(self.rank - 1), self.group))
+                ops.append(dist.P2POp(dist.irecv, self._recv_up[k], self._peer(self.rank - 1), self.group))
+            if p.bottom:
+                ops.append(dist.P2POp(dist.isend, acc[pl, hl - p.bottom:], self._peer(self.rank + 1), self.group))
+                ops.append(dist.P2POp(dist.irecv, self._recv_dn[k], self._peer(self.rank + 1), self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        if events is not None:
+            events[0].record(torch.cuda.current_stream(self.device))
         if p.top:       # neighbour's bottom halo = my rows [top, 2*top)
-            self.backend.merge(acc[:, p.top:2 * p.top], self._recv_up)
-            self.backend.finalize(self.local_spec, acc, p.top, 2 * p.top, {"image": out["image"]})
+            self.backend.merge_finalize(self.local_spec, acc, p.top, 2 * p.top, self._recv_up, self.planes, {"image": out["image"]})
         if p.bottom:
-            self.backend.merge(acc[:, hl - 2 * p.bottom:hl - p.bottom], self._recv_dn)
-            self.backend.finalize(self.local_spec, acc, hl - 2 * p.bottom, hl - p.bottom, {"image": out["image"]})
+            self.backend.merge_finalize(self.local_spec, acc, hl - 2 * p.bottom, hl - p.bottom, self._recv_dn, self.planes,
+                                        {"image": out["image"]})
 
     # -- pipelined steps: rasterise scene k while scene k-1's mosaic is still being gathered -----------
     def step(self, points: torch.Tensor) -> int:
@@ -189,22 +193,86 @@ class StripRasterizer:
         if self._gather_done[k] is not None:
             main.wait_event(self._gather_done[k])          # the strip buffer is free once its gather has run
         p = self.plan
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if self.time_stages else None
+        if ev:
+            ev[0].record(main)
         out = self.raster(points, out=self._outs[k])
         hl = self.local_spec.height
         strip = out["image"][p.top:hl - p.bottom]
-        ready = torch.cuda.Event()
+        ready = torch.cuda.Event(enable_timing=self.time_stages)
         ready.record(main)
         with torch.cuda.stream(self._comm_stream):
             # everything after the local rasterisation -- halo exchange, merge, re-finish of the edge
             # bands, mosaic gather -- runs on the side stream, under the next scene's rasterisation
             self._comm_stream.wait_event(ready)
+            if ev:
+                ev[1].record(self._comm_stream)
             if self.need_acc:
-                self._exchange_and_merge(out)
-            self._mosaics[k] = self.gather(strip, self.gather_root)
-            done = torch.cuda.Event()
+                self._exchange_and_merge(out, ev[2:3] if ev else None)
+            elif ev:
+                ev[2].record(self._comm_stream)
+            if ev:
+                ev[3].record(self._comm_stream)
+            self._mosaics[k] = self.gather(strip, self.gather_root) if self.gather_root != "none" else None
+            done = torch.cuda.Event(enable_timing=self.time_stages)
             done.record(self._comm_stream)
+        if ev:
+            self._stage_events.append((ev[0], ready, ev[1], ev[2], ev[3], done))
+            del self._stage_events[:-64]
         self._gather_done[k] = done
         return k
+
+    def stage_times(self) -> Dict[str, float]:
+        """Mean ms of the stages of the last ``step()`` calls (``time_stages=True``; synchronises): local
+        rasterisation (main stream), then on the side stream halo exchange, merge + re-finish, mosaic gather."""
+        if not self._stage_events:
+            return {}
+        torch.cuda.synchronize(self.device)
+        n = len(self._stage_events)
+        acc = {"raster": 0.0, "halo_exchange": 0.0, "merge_finalize": 0.0, "gather": 0.0, "side_stream_total": 0.0}
+        for e0, ready, c0, c1, c2, done in self._stage_events:
+            acc["raster"] += e0.elapsed_time(ready)
+            acc["halo_exchange"] += c0.elapsed_time(c1)
+            acc["merge_finalize"] += c1.elapsed_time(c2)
+            acc["gather"] += c2.elapsed_time(done)
+            acc["side_stream_total"] += c0.elapsed_time(done)
+        return {k: v / n for k, v in acc.items()}
+
+    def verify(self, points: torch.Tensor, strip: torch.Tensor) -> int:
+        """Independent check of a finished strip (bytes that differ): the global-atomic algorithm
+        (``LM_ALGO_DIRECT``) on this rank's window, ALL six raw planes of the halo rows exchanged as packed
+        copies, merged with plain torch integer ops (the merge law of SURVEY 8e), finished with ``lm_bev_finalize``."""
+        from .bev import BevRasterizer, finalize_rows
+        p, hl, W = self.plan, self.local_spec.height, self.spec.width
+        d = BevRasterizer(self.local_spec, max(int(points.shape[0]), 1), device=self.device, algo="direct", outputs=("image", "acc"))
+        o = d(points)
+        acc = o["acc"]
+        if self.need_acc:
+            ops, bufs = [], {}
+            for name, rows, peer in (("up", slice(0, p.top), self.rank - 1), ("dn", slice(hl - p.bottom, hl), self.rank + 1)):
+                n = p.top if name == "up" else p.bottom
+                if not n:
+                    continue
+                snd = acc[:, rows].contiguous()
+                rcv = torch.empty_like(snd)
+                bufs[name] = (snd, rcv)
+                ops.append(dist.P2POp(dist.isend, snd, self._peer(peer), self.group))
+                ops.append(dist.P2POp(dist.irecv, rcv, self._peer(peer), self.group))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for name, (snd, rcv) in bufs.items():
+                band = slice(p.top, 2 * p.top) if name == "up" else slice(hl - 2 * p.bottom, hl - p.bottom)
+                a = acc[:, band].to(torch.int64) & 0xFFFFFFFF
+                b = rcv.to(torch.int64) & 0xFFFFFFFF
+                m = torch.empty_like(a)
+                m[0:3] = a[0:3] + b[0:3]                       # count, sum_i, sum_z
+                m[3] = torch.maximum(a[3], b[3])               # max_i
+                m[4] = torch.minimum(a[4], b[4])               # min_z (0xFFFFFFFF where empty)
+                m[5] = torch.maximum(a[5], b[5])               # max_z
+                acc[:, band] = torch.where(m >= 2 ** 31, m - 2 ** 32, m).to(torch.int32)
+                finalize_rows(self.local_spec, acc, band.start, band.stop, {"image": o["image"]})
+        want = o["image"][p.top:hl - p.bottom]
+        return int((want != strip).sum().item())
 
     def mosaic(self, slot: int) -> Optional[torch.Tensor]:
         """The scene's mosaic (None on the ranks a rooted gather leaves empty); the current stream waits

@@ -1,6 +1,7 @@
-"""GPU, >= 2 devices: strip-sharded rasterisation over NCCL (halo merge + mosaic gather) equals the
-single-GPU one-piece raster bit for bit.  Skipped on single-GPU boxes (the gloo tests cover the
-host logic there)."""
+"""GPU, >= 2 devices: strip-sharded rasterisation over NCCL (plane-wise halo exchange, fused merge + re-finish,
+mosaic gather) equals the ORACLE's one-piece raster bit for bit (and the single-GPU CUDA raster, and the
+independent DIRECT-algorithm check of ``StripRasterizer.verify``).  Skipped on single-GPU boxes (the gloo
+tests cover the host logic there; bench.py --gpus N runs the same verification on every scaling run)."""
 import os
 import socket
 import sys
@@ -35,6 +36,10 @@ def _worker(rank, world, port, q):
         strip = sr.rasterize(mine)
         mosaic = sr.gather(strip)
         one = BevRasterizer(spec, len(cloud), outputs=("image",))(torch.from_numpy(cloud).cuda())["image"]
+        from oracle import c_oracle as CO
+        want = torch.from_numpy(CO.rasterize(cloud, spec)["image"]).cuda()          # the oracle, not only CUDA vs CUDA
+        ok_oracle = bool(torch.equal(mosaic, want)) and bool(torch.equal(one, want)) and sr.verify(mine, strip) == 0
+        assert sr.planes == [0, 2, 3] and sr.halo_bytes == 3 * 64 * 1152 * 4       # count, sum_z, max_i only
         # pipelined form: three scenes in flight through the two buffer slots
         slots = [sr.step(mine) for _ in range(3)]
         piped = sr.mosaic(slots[-1]).clone()
@@ -50,7 +55,7 @@ def _worker(rank, world, port, q):
         ok_root = ok_root and (bool(torch.equal(m2, one)) if rank == 0 else m2 is None) and bool(torch.equal(sr2.strip_of(s2[-1]), one[a:b]))
         sr2.flush()
         torch.cuda.synchronize()
-        ok = bool(torch.equal(mosaic, one)) and bool(torch.equal(piped, one)) and slots == [0, 1, 0] and ok_root
+        ok = bool(torch.equal(mosaic, one)) and bool(torch.equal(piped, one)) and slots == [0, 1, 0] and ok_root and ok_oracle
         q.put((rank, ok, int(mine.shape[0])))
     finally:
         dist.destroy_process_group()
