@@ -16,7 +16,8 @@
  *   - return value: 0 = OK; <0 = argument error detected before any launch (LM_ERR_*);
  *     >0 = the cudaError_t of a failed launch.  lm_bev_last_error() gives the message
  *     for the calling thread.  Re-entrant: no global mutable state besides that
- *     thread-local message.
+ *     thread-local message; no environment variables are read (tuning knobs are fields of
+ *     lm_bev_tuning, passed through a plan).
  *   - device-side conditions that cannot be known before launch (workspace chunk pool
  *     exhausted, per-cell count above the u32-sum limit) are reported in lm_bev_stats.error,
  *     which lives at the start of the workspace.
@@ -162,6 +163,32 @@ enum { LM_STAGE_BIN = 1, LM_STAGE_INDEX = 2, LM_STAGE_REDUCE = 4, LM_STAGE_SWEEP
 int lm_bev_rasterize_stages(const lm_bev_params *p, const float *points_dev, int64_t n_points, int algo,
                             void *workspace_dev, size_t workspace_bytes,
                             const lm_bev_outputs *out, void *stream, int stages);
+
+/* ---- Plan: a stream of equally-shaped calls.  Holds what is fixed (geometry, output set, algorithm, tuning) and,
+ * with tuning.use_graph, a CUDA graph of the launch sequence that is replayed while a call repeats the previous
+ * call's arguments (same buffers, same n_points: the steady state of a pipeline with preallocated buffers) -- one
+ * graph launch instead of a memset and 4..6 kernel launches, which is what bounds the small configs.
+ * The library reads no environment variables: every knob is a field here (0 = default).  A plan is used by one
+ * thread at a time; it owns no device memory (a capture stream and the graph only).                          */
+typedef struct lm_bev_tuning {
+    int32_t bin_ctas_per_sm;   /* bin_points CTAs per SM (default: what fits, 3 on rasters wider than 36 tiles)  */
+    int32_t red_ctas_per_sm;   /* reduce_tiles CTAs per SM (default: what fits)                                  */
+    int32_t tile_h_log2;       /* shared-memory tile height 2^5..2^7 rows (default: by plane count / raster size) */
+    int32_t max_tiles;         /* tiles per launch; smaller values force the in-call row-window loop (tests)     */
+    int32_t stream_hint;       /* 1: the point stream is loaded with an L2 evict-first policy                    */
+    int32_t use_graph;         /* 1: lm_bev_plan_rasterize replays a captured graph while the arguments repeat   */
+    int32_t reserved[2];
+} lm_bev_tuning;
+typedef struct lm_bev_plan lm_bev_plan;
+
+/* out_set: which outputs the calls will request (pointer NULL-ness + acc_band; the pointers themselves are not kept). */
+int lm_bev_plan_create(const lm_bev_params *p, int64_t max_points, int algo, const lm_bev_outputs *out_set,
+                       const lm_bev_tuning *tuning /* NULL = defaults */, lm_bev_plan **plan);
+int lm_bev_plan_workspace_bytes(const lm_bev_plan *plan, size_t *bytes);
+int lm_bev_plan_init_workspace(lm_bev_plan *plan, void *workspace_dev, size_t workspace_bytes, void *stream);
+int lm_bev_plan_rasterize(lm_bev_plan *plan, const float *points_dev, int64_t n_points, void *workspace_dev,
+                          size_t workspace_bytes, const lm_bev_outputs *out, void *stream);
+int lm_bev_plan_destroy(lm_bev_plan *plan);
 
 /* Batched call (BASELINE.json configs[4]: on-the-fly rasterisation of a DataLoader batch into
  * sample['proj'], reference baseline/models/pcencoder/postprojector.py:79-82).  n_samples clouds

@@ -39,6 +39,11 @@ class LmBevOutputs(C.Structure):
     ]
 
 
+class LmBevTuning(C.Structure):
+    _fields_ = [("bin_ctas_per_sm", C.c_int32), ("red_ctas_per_sm", C.c_int32), ("tile_h_log2", C.c_int32),
+                ("max_tiles", C.c_int32), ("stream_hint", C.c_int32), ("use_graph", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
 class LmBevSampleGeom(C.Structure):
     _fields_ = [
         ("bev_img_offset", C.c_float * 2),
@@ -90,6 +95,13 @@ SYMBOLS = {
     "lm_bev_workspace_init": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(LmBevOutputs), C.c_void_p,
                                         C.c_size_t, C.c_void_p]),
     "lm_bev_sweep_state_offset": (C.c_int, [C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lm_bev_plan_create": (C.c_int, [C.POINTER(LmBevParams), C.c_int64, C.c_int, C.POINTER(LmBevOutputs),
+                                     C.POINTER(LmBevTuning), C.POINTER(C.c_void_p)]),
+    "lm_bev_plan_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "lm_bev_plan_init_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lm_bev_plan_rasterize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.POINTER(LmBevOutputs),
+                                        C.c_void_p]),
+    "lm_bev_plan_destroy": (C.c_int, [C.c_void_p]),
     "lm_bev_rasterize": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,
                                    C.POINTER(LmBevOutputs), C.c_void_p]),
     "lm_bev_rasterize_stages": (C.c_int, [C.POINTER(LmBevParams), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t,

@@ -52,7 +52,11 @@ class BevRasterizer:
     """
 
     def __init__(self, spec: BevSpec, max_points: int, device: torch.device | str = "cuda",
-                 algo: str = "binned", outputs: Iterable[str] = ("image",), acc_band: int = 0):
+                 algo: str = "binned", outputs: Iterable[str] = ("image",), acc_band: int = 0,
+                 tuning: Optional[Dict[str, int]] = None, graph: bool = False):
+        """``tuning``: fields of ``lm_bev_tuning`` (include/lm_bev.h), e.g. ``{"bin_ctas_per_sm": 3}``; ``graph=True``:
+        a call that repeats the previous call's buffers and point count replays a captured CUDA graph (one launch
+        instead of a memset and 4..6 kernels: what bounds the small configs)."""
         if algo not in ALGOS:
             raise ValueError(f"algo must be one of {sorted(ALGOS)}")
         outputs = tuple(outputs)
@@ -70,15 +74,34 @@ class BevRasterizer:
         self.max_points = int(max_points)
         self._params = _cabi.make_params(spec)
         self._lib = _cabi.lib()
-        self.workspace = torch.empty(workspace_bytes(spec, self.max_points, algo, outputs, self.acc_band),
-                                     dtype=torch.uint8, device=self.device)
+        self._tuning = _cabi.LmBevTuning()
+        for k, v in (tuning or {}).items():
+            if not hasattr(self._tuning, k) or k == "reserved":
+                raise ValueError(f"unknown tuning field {k!r}")
+            setattr(self._tuning, k, int(v))
+        if graph:
+            self._tuning.use_graph = 1
+        self._plan = C.c_void_p()
+        o = self._sizing_outputs()
+        _cabi.check(self._lib.lm_bev_plan_create(C.byref(self._params), self.max_points, ALGOS[algo], C.byref(o),
+                                                 C.byref(self._tuning), C.byref(self._plan)))
+        nbytes = C.c_size_t(0)
+        _cabi.check(self._lib.lm_bev_plan_workspace_bytes(self._plan, C.byref(nbytes)))
+        self.workspace = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.device)
         if algo == "sweep":
             # the sweep's mailboxes keep state between calls: prepare them once (include/lm_bev.h)
-            o = self._sizing_outputs()
             with torch.cuda.device(self.device):
-                _cabi.check(self._lib.lm_bev_workspace_init(C.byref(self._params), self.max_points, ALGOS[algo], C.byref(o),
-                                                            self.workspace.data_ptr(), self.workspace.numel(),
-                                                            torch.cuda.current_stream(self.device).cuda_stream))
+                _cabi.check(self._lib.lm_bev_plan_init_workspace(self._plan, self.workspace.data_ptr(), self.workspace.numel(),
+                                                                 torch.cuda.current_stream(self.device).cuda_stream))
+
+    def __del__(self):
+        plan, lib = getattr(self, "_plan", None), getattr(self, "_lib", None)
+        if plan and lib is not None:
+            try:
+                lib.lm_bev_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
 
     def _sizing_outputs(self) -> "_cabi.LmBevOutputs":
         o = _cabi.LmBevOutputs()
@@ -138,9 +161,14 @@ class BevRasterizer:
         o.acc_band = self.acc_band
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.lm_bev_rasterize_stages(
-                C.byref(self._params), points.data_ptr() if n else None, n, ALGOS[self.algo],
-                self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream, int(stages)))
+            if int(stages) == _cabi.STAGE_ALL:
+                _cabi.check(self._lib.lm_bev_plan_rasterize(
+                    self._plan, points.data_ptr() if n else None, n, self.workspace.data_ptr(), self.workspace.numel(),
+                    C.byref(o), st.cuda_stream))
+            else:       # stage-split calls (per-kernel timing): the plain entry point, default tuning
+                _cabi.check(self._lib.lm_bev_rasterize_stages(
+                    C.byref(self._params), points.data_ptr() if n else None, n, ALGOS[self.algo],
+                    self.workspace.data_ptr(), self.workspace.numel(), C.byref(o), st.cuda_stream, int(stages)))
         return out
 
     def rasterize_las(self, records: torch.Tensor, n_points: int, xform, out: Optional[Dict[str, torch.Tensor]] = None,
@@ -183,65 +211,6 @@ class BevRasterizer:
             raise RuntimeError("liblm_bev: record chunk pool exhausted (workspace too small)")
         if s["error"] & _cabi.DEV_ERR_CELL_OVERFLOW:
             raise RuntimeError("liblm_bev: a cell received >= 2^24 points; u32 sums may have wrapped")
-
-
-class PipelinedRasterizer:
-    """Throughput mode for a stream of equally-shaped scenes -- EXPERIMENTAL, not yet measured
-    (DESIGN.md section 9): ``bin_points`` of scene k+1 runs on one stream while ``index`` +
-    ``reduce_tiles`` of scene k run on another, through the stage-split C-ABI entry.  ``bin_points`` is
-    HBM-bound and ``reduce_tiles`` shared-memory-atomic-bound, so the two can share the SMs; for them to be
-    co-resident the grids have to leave room for each other (``LM_BEV_BIN_CTAS_PER_SM=2``,
-    ``LM_BEV_RED_CTAS_PER_SM=1`` fit the register file and shared memory of an SM together).
-    Two workspaces and two output sets: at most two scenes are in flight, slot k % 2 is reused by
-    scene k + 2."""
-
-    def __init__(self, spec: BevSpec, max_points: int, device: torch.device | str = "cuda",
-                 outputs: Iterable[str] = ("image",)):
-        self.rasters = [BevRasterizer(spec, max_points, device=device, algo="binned", outputs=outputs) for _ in range(2)]
-        self.device = self.rasters[0].device
-        self.outs = [r.alloc_outputs() for r in self.rasters]
-        self.s_bin = torch.cuda.Stream(self.device)
-        self.s_red = torch.cuda.Stream(self.device)
-        self._done = [None, None]
-        self._k = 0
-
-    def submit(self, points: torch.Tensor) -> int:
-        """Enqueue one scene; returns its slot.  ``points`` must stay unchanged until the scene is done."""
-        slot = self._k % 2
-        self._k += 1
-        cur = torch.cuda.current_stream(self.device)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        self.s_bin.wait_event(ready)                       # the caller's stream produced the points
-        if self._done[slot] is not None:
-            self.s_bin.wait_event(self._done[slot])        # workspace and outputs of scene k - 2 are free
-        r, out = self.rasters[slot], self.outs[slot]
-        points.record_stream(self.s_bin)
-        r(points, out=out, stream=self.s_bin, stages=_cabi.STAGE_BIN)
-        binned = torch.cuda.Event()
-        binned.record(self.s_bin)
-        self.s_red.wait_event(binned)
-        r(points, out=out, stream=self.s_red, stages=_cabi.STAGE_INDEX)
-        r(points, out=out, stream=self.s_red, stages=_cabi.STAGE_REDUCE)
-        done = torch.cuda.Event()
-        done.record(self.s_red)
-        self._done[slot] = done
-        return slot
-
-    def result(self, slot: int) -> Dict[str, torch.Tensor]:
-        """The scene's outputs; the current stream waits for its reduce."""
-        torch.cuda.current_stream(self.device).wait_event(self._done[slot])
-        return self.outs[slot]
-
-    def flush(self) -> None:
-        cur = torch.cuda.current_stream(self.device)
-        for d in self._done:
-            if d is not None:
-                cur.wait_event(d)
-
-    def check_device_errors(self) -> None:
-        for r in self.rasters:
-            r.check_device_errors()
 
 
 class BatchRasterizer:

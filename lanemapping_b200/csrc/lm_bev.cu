@@ -30,6 +30,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <new>
 
 namespace {
 extern thread_local char g_err[512];
@@ -151,6 +152,15 @@ struct Outs {
 };
 
 thread_local char g_err[512] = "";
+// Tuning knobs of the call in progress (a plan's, include/lm_bev.h lm_bev_tuning; all-zero = defaults for the
+// plain entry points).  Nothing in the library reads the process environment.
+const lm_bev_tuning k_default_tuning = {0, 0, 0, 0, 0, 0, {0, 0}};
+thread_local const lm_bev_tuning *g_tune = &k_default_tuning;
+struct TuneScope {
+    const lm_bev_tuning *prev;
+    explicit TuneScope(const lm_bev_tuning *t) : prev(g_tune) { g_tune = t ? t : &k_default_tuning; }
+    ~TuneScope() { g_tune = prev; }
+};
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -360,17 +370,34 @@ __global__ void merge_finalize_kernel(KParams kp, uint32_t *acc, int r0, int r1,
     }
 }
 
+// One thread moves 16 consecutive bytes of a crop row (a crop row = tile * C bytes of one mosaic row, or zeros
+// beyond a ragged edge).  VEC: source and destination are 16-byte aligned for every piece (tile * C, W * C
+// multiples of 16 and aligned bases), so both sides are single 128-bit accesses; else bytes.
+template <bool VEC>
 __global__ void crop_tiles_kernel(const uint8_t *__restrict__ img, int H, int W, int C, int tile, int ncx,
-                                  uint8_t *__restrict__ crops, size_t total) {
-    const size_t row_bytes = (size_t)tile * C;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i % row_bytes;           // byte inside the crop row
-        const size_t rr = i / row_bytes;          // crop * tile + r
+                                  uint8_t *__restrict__ crops, size_t total16) {
+    const size_t row_bytes = (size_t)tile * C;                 // bytes of one crop row
+    const size_t pieces = (row_bytes + 15) / 16;               // 16-byte pieces per crop row (the last may be short)
+    const size_t mosaic_row = (size_t)W * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total16; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pc = i % pieces;
+        const size_t rr = i / pieces;                           // crop * tile + r
         const int r = (int)(rr % tile);
         const int crop = (int)(rr / tile);
         const int gy = (crop / ncx) * tile + r;
-        const size_t gxb = (size_t)(crop % ncx) * row_bytes + b;   // byte inside the mosaic row
-        crops[i] = (gy < H && gxb < (size_t)W * C) ? img[(size_t)gy * W * C + gxb] : (uint8_t)0;
+        const size_t b0 = pc * 16;                              // first byte of the piece inside the crop row
+        const size_t gxb = (size_t)(crop % ncx) * row_bytes + b0;
+        uint8_t *dst = crops + rr * row_bytes + b0;
+        const size_t len = row_bytes - b0 < 16 ? row_bytes - b0 : 16;
+        const bool inside = gy < H && gxb + len <= mosaic_row;
+        if (VEC) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (inside) v = __ldcs(reinterpret_cast<const uint4 *>(img + (size_t)gy * mosaic_row + gxb));
+            __stcs(reinterpret_cast<uint4 *>(dst), v);
+        } else {
+            for (size_t k = 0; k < len; ++k)
+                dst[k] = (gy < H && gxb + k < mosaic_row) ? img[(size_t)gy * mosaic_row + gxb + k] : (uint8_t)0;
+        }
     }
 }
 
@@ -1181,8 +1208,7 @@ int sm_count() { return lm_sm_count(); }
 // persistent reduce CTAs of every SM get a few tiles each.
 int tile_h_log2_for(int mask, int height, int width) {
     const int nw = popc6(mask);
-    if (const char *e = getenv("LM_BEV_TILE_H_LOG2")) {      // tuning knob (5..7); must keep NW planes <= 227 KB
-        const int v = atoi(e);
+    if (const int v = g_tune->tile_h_log2) {                  // tuning knob (5..7); must keep NW planes <= 227 KB
         if (v >= 5 && v <= 7 && nw * (128 << v) * 4 <= 200 * 1024) return v;
     }
     int th = nw <= 1 ? 7 : 6;      // 128 x 64 tiles: 2 CTAs/SM up to 3 planes, 1 CTA/SM (<= 192 KB) up to 6
@@ -1211,8 +1237,7 @@ int validate(const lm_bev_params *p) {
 
 // L2 policy of the point stream in bin_points (LM_BEV_STREAM_HINT=0/1 overrides; measured in profiles/)
 int stream_hint_default() {
-    if (const char *e = getenv("LM_BEV_STREAM_HINT")) return atoi(e) & 1;
-    return 0;
+    return g_tune->stream_hint & 1;
 }
 
 KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
@@ -1269,8 +1294,7 @@ int bin_ctas_bound(int T) {
 }
 
 int max_tiles() {
-    if (const char *e = getenv("LM_BEV_MAX_TILES")) {      // test knob: forces the row-window loop on small rasters
-        const int v = atoi(e);
+    if (const int v = g_tune->max_tiles) {                  // test knob: forces the row-window loop on small rasters
         if (v >= 1 && v <= MAX_TILES) return v;
     }
     return MAX_TILES;
@@ -1411,8 +1435,7 @@ int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles
     // 11520-column strips of config 3 (profiles/r01_v11_hint_sweep.txt), the full wave on config 2.
     const int hw_occ = occ;
     if (tiles_x > 36 && occ > 3) occ = 3;
-    if (const char *ev = getenv("LM_BEV_BIN_CTAS_PER_SM")) {      // tuning knob, 1 .. what the hardware holds
-        const int v = atoi(ev);
+    if (const int v = g_tune->bin_ctas_per_sm) {                  // tuning knob, 1 .. what the hardware holds
         if (v >= 1) occ = v < hw_occ ? v : hw_occ;
     }
     long long grid = (long long)sms * (occ < 1 ? 1 : occ);
@@ -1440,8 +1463,7 @@ cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sm
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK>, RED_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
-    if (const char *ev = getenv("LM_BEV_RED_CTAS_PER_SM")) {      // tuning knob: leave room for a concurrent bin_points
-        const int v = atoi(ev);
+    if (const int v = g_tune->red_ctas_per_sm) {                  // tuning knob
         if (v >= 1 && v < occ) occ = v;
     }
     const int grid = kp.T < sms * occ ? kp.T : sms * occ;
@@ -1892,6 +1914,106 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
     return LM_OK;
 }
 
+// ---- plan: everything that is fixed for a stream of equally-shaped calls (include/lm_bev.h)
+struct lm_bev_plan {
+    lm_bev_params params;
+    int64_t max_points;
+    int algo;
+    lm_bev_outputs out_set;          // only which pointers are non-NULL (and acc_band) matter
+    lm_bev_tuning tuning;
+    size_t workspace_bytes;
+    // CUDA graph of the last call's launch sequence, replayed while the arguments repeat
+    cudaStream_t cap_stream;
+    cudaGraphExec_t exec;
+    const float *k_points;
+    int64_t k_n;
+    void *k_ws;
+    size_t k_ws_bytes;
+    lm_bev_outputs k_out;
+};
+
+int lm_bev_plan_create(const lm_bev_params *p, int64_t max_points, int algo, const lm_bev_outputs *out_set,
+                       const lm_bev_tuning *tuning, lm_bev_plan **plan) {
+    if (!plan) return fail(LM_ERR_INVALID, "plan is NULL");
+    *plan = nullptr;
+    if (!out_set) return fail(LM_ERR_INVALID, "out_set is NULL (which outputs the calls will ask for fixes the tile shape)");
+    TuneScope ts(tuning);
+    size_t bytes = 0;
+    int rc = lm_bev_workspace_bytes(p, max_points, algo, out_set, &bytes);
+    if (rc) return rc;
+    lm_bev_plan *pl = new (std::nothrow) lm_bev_plan();
+    if (!pl) return fail(LM_ERR_INVALID, "out of host memory");
+    pl->params = *p;
+    pl->max_points = max_points;
+    pl->algo = algo;
+    pl->out_set = *out_set;
+    pl->tuning = tuning ? *tuning : k_default_tuning;
+    pl->workspace_bytes = bytes;
+    pl->cap_stream = nullptr;
+    pl->exec = nullptr;
+    pl->k_points = nullptr;
+    pl->k_n = -1;
+    pl->k_ws = nullptr;
+    pl->k_ws_bytes = 0;
+    memset(&pl->k_out, 0, sizeof(pl->k_out));
+    *plan = pl;
+    return LM_OK;
+}
+
+int lm_bev_plan_workspace_bytes(const lm_bev_plan *plan, size_t *bytes) {
+    if (!plan || !bytes) return fail(LM_ERR_INVALID, "plan/bytes is NULL");
+    *bytes = plan->workspace_bytes;
+    return LM_OK;
+}
+
+int lm_bev_plan_init_workspace(lm_bev_plan *plan, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (!plan) return fail(LM_ERR_INVALID, "plan is NULL");
+    TuneScope ts(&plan->tuning);
+    return lm_bev_workspace_init(&plan->params, plan->max_points, plan->algo, &plan->out_set, workspace_dev, workspace_bytes, stream);
+}
+
+int lm_bev_plan_rasterize(lm_bev_plan *plan, const float *points_dev, int64_t n_points, void *workspace_dev,
+                          size_t workspace_bytes, const lm_bev_outputs *out, void *stream) {
+    if (!plan || !out) return fail(LM_ERR_INVALID, "plan/out is NULL");
+    if (n_points > plan->max_points) return fail(LM_ERR_INVALID, "n_points exceeds the plan's max_points");
+    TuneScope ts(&plan->tuning);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!plan->tuning.use_graph)
+        return rasterize_impl(&plan->params, points_dev, n_points, plan->algo, workspace_dev, workspace_bytes, out, stream,
+                              LM_STAGE_ALL, false);
+    // same arguments as the captured call: one graph launch replaces the memset + kernel launches
+    const bool same = plan->exec && plan->k_points == points_dev && plan->k_n == n_points && plan->k_ws == workspace_dev &&
+                      plan->k_ws_bytes == workspace_bytes && memcmp(&plan->k_out, out, sizeof(*out)) == 0;
+    if (!same) {
+        cudaError_t e = cudaSuccess;
+        if (!plan->cap_stream && (e = cudaStreamCreateWithFlags(&plan->cap_stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(e, "plan stream");
+        if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
+        if ((e = cudaStreamBeginCapture(plan->cap_stream, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return cuda_fail(e, "begin capture");
+        const int rc = rasterize_impl(&plan->params, points_dev, n_points, plan->algo, workspace_dev, workspace_bytes, out,
+                                      plan->cap_stream, LM_STAGE_ALL, false);
+        cudaGraph_t g = nullptr;
+        e = cudaStreamEndCapture(plan->cap_stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return cuda_fail(e, "end capture");
+        e = cudaGraphInstantiate(&plan->exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { plan->exec = nullptr; return cuda_fail(e, "graph instantiate"); }
+        plan->k_points = points_dev; plan->k_n = n_points; plan->k_ws = workspace_dev; plan->k_ws_bytes = workspace_bytes;
+        plan->k_out = *out;
+    }
+    cudaError_t e = cudaGraphLaunch(plan->exec, st);
+    return e == cudaSuccess ? LM_OK : cuda_fail(e, "graph launch");
+}
+
+int lm_bev_plan_destroy(lm_bev_plan *plan) {
+    if (!plan) return LM_OK;
+    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
+    delete plan;
+    return LM_OK;
+}
+
 int lm_bev_acc_merge(uint32_t *dst, int64_t dstride, const uint32_t *src, int64_t sstride, int32_t rows,
                      int32_t width, void *stream) {
     if (!dst || !src || rows < 0 || width <= 0) return fail(LM_ERR_INVALID, "bad acc_merge arguments");
@@ -1936,8 +2058,14 @@ int lm_bev_crop_tiles(const uint8_t *image_dev, int32_t height, int32_t width, i
     if (!image_dev || !crops_dev || height <= 0 || width <= 0 || c < 1 || c > 4 || tile <= 0)
         return fail(LM_ERR_INVALID, "bad crop_tiles arguments");
     const int ncy = (height + tile - 1) / tile, ncx = (width + tile - 1) / tile;
-    const size_t total = (size_t)ncy * ncx * tile * tile * c;
-    crop_tiles_kernel<<<sm_count() * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(image_dev, height, width, c, tile, ncx, crops_dev, total);
+    const size_t row_bytes = (size_t)tile * c, pieces = (row_bytes + 15) / 16;
+    const size_t total16 = (size_t)ncy * ncx * tile * pieces;
+    // 128-bit path: every piece of both buffers is 16-byte aligned and whole (1152 px crops of 1..4 channels are)
+    const bool vec = row_bytes % 16 == 0 && ((size_t)width * c) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(image_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(crops_dev) & 15) == 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (vec) crop_tiles_kernel<true><<<sm_count() * 8, 256, 0, st>>>(image_dev, height, width, c, tile, ncx, crops_dev, total16);
+    else crop_tiles_kernel<false><<<sm_count() * 8, 256, 0, st>>>(image_dev, height, width, c, tile, ncx, crops_dev, total16);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? LM_OK : cuda_fail(e, "crop_tiles launch");
 }

@@ -222,6 +222,11 @@ class StripRasterizer:
         self._gather_done[k] = done
         return k
 
+    def reset_stage_times(self) -> None:
+        """Forget the recorded steps (call after warm-up: the first steps carry NCCL's connection set-up)."""
+        torch.cuda.synchronize(self.device)
+        self._stage_events.clear()
+
     def stage_times(self) -> Dict[str, float]:
         """Mean ms of the stages of the last ``step()`` calls (``time_stages=True``; synchronises): local
         rasterisation (main stream), then on the side stream halo exchange, merge + re-finish, mosaic gather."""

@@ -25,14 +25,13 @@ def bev(native_lib):
 
 @pytest.mark.parametrize("channels,count16", [((CH_MAX_I, CH_MEAN_Z, CH_DENSITY), False),
                                               ((CH_MAX_I, CH_MIN_Z, CH_MEAN_I, CH_MAX_Z), True)])
-def test_row_window_loop_is_bit_exact(bev, monkeypatch, channels, count16):
+def test_row_window_loop_is_bit_exact(bev, channels, count16):
     """Force the in-call row-window loop (as config 4's 24 300 tiles would) on a small raster."""
     spec = BevSpec(700, 300, img_reso=(0.1, 0.1), channels=channels, count16=count16, local_min_ele=-2.0)
     cloud = make_cloud(600_000, spec, seed=31, order="scan")
     want = O.rasterize(cloud, spec)
-    monkeypatch.setenv("LM_BEV_MAX_TILES", "7")          # 3 tiles per tile row -> 2 tile rows per window
     outs = ["image", "proj", "acc"] + (["count16"] if count16 else [])
-    r = bev.BevRasterizer(spec, len(cloud), outputs=outs)
+    r = bev.BevRasterizer(spec, len(cloud), outputs=outs, tuning={"max_tiles": 7})   # 3 tiles per tile row -> 2 tile rows per window
     got = r(torch.from_numpy(cloud).cuda())
     torch.cuda.synchronize()
     st = r.stats()

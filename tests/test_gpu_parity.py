@@ -252,23 +252,27 @@ def test_exact_mean_exhaustive(bev, native_lib):
     assert n == sum(255 * c + 1 for c in range(1, 4096)) and bad == 0
 
 
-def test_pipelined_rasterizer_matches_oracle(bev):
-    # two-stream mode (bev.PipelinedRasterizer): bin_points of scene k+1 on one stream, index + reduce_tiles of
-    # scene k on another -- every scene's raster must still be the oracle's, whatever the interleaving
-    # (the same scenes as tools/try_pipeline.py, checked here against the C restatement)
+def test_plan_graph_replay_and_tuning_fields(bev):
+    """BevRasterizer runs on the plan API (include/lm_bev.h): with ``graph=True`` a call that repeats the previous
+    call's buffers replays a captured CUDA graph, a call with other buffers re-captures; the tuning knobs are plan
+    fields (the library reads no environment variables) and never change a result."""
     from oracle import c_oracle as CO
     spec = BevSpec(1152, 1152, local_min_ele=default_min_ele(BevSpec(1152, 1152)))
-    clouds = [make_cloud(800_000 + 50_000 * i, spec, seed=70 + i, order="scan" if i % 2 else "shuffled") for i in range(4)]
+    clouds = [make_cloud(600_000 + 10_000 * i, spec, seed=70 + i, order="scan" if i % 2 else "shuffled") for i in range(3)]
     want = [CO.rasterize(c, spec)["image"] for c in clouds]
     dev = [torch.from_numpy(c).cuda() for c in clouds]
-    pr = bev.PipelinedRasterizer(spec, max(len(c) for c in clouds))
-    slots = [pr.submit(d) for d in dev]
-    assert slots == [0, 1, 0, 1]
-    for i in (2, 3):                       # the last two scenes are still in their slots
-        assert np.array_equal(pr.result(slots[i])["image"].cpu().numpy(), want[i])
-    for i in (0, 1):
-        s = pr.submit(dev[i])
-        assert np.array_equal(pr.result(s)["image"].cpu().numpy(), want[i])
-    pr.flush()
-    torch.cuda.synchronize()
-    pr.check_device_errors()
+    r = bev.BevRasterizer(spec, max(len(c) for c in clouds), graph=True)
+    out = r.alloc_outputs()
+    for rep in range(3):                                   # same arguments: capture once, replay twice
+        out["image"].fill_(9)
+        r(dev[0], out=out)
+        assert np.array_equal(out["image"].cpu().numpy(), want[0])
+    for i in (1, 2, 0):                                    # other points / sizes: re-captured, still exact
+        got = r(dev[i], out=out)
+        assert np.array_equal(got["image"].cpu().numpy(), want[i])
+    r.check_device_errors()
+    for tuning in ({"bin_ctas_per_sm": 2, "red_ctas_per_sm": 1}, {"tile_h_log2": 5, "stream_hint": 1}, {"max_tiles": 20}):
+        rt = bev.BevRasterizer(spec, len(clouds[1]), tuning=tuning)
+        assert np.array_equal(rt(dev[1])["image"].cpu().numpy(), want[1]), tuning
+    with pytest.raises(ValueError):
+        bev.BevRasterizer(spec, 10, tuning={"no_such_knob": 1})
