@@ -132,7 +132,9 @@ class StripRasterizer:
         self._mosaics = [None, None]
         self._gather_done = [None, None]
         self._comm_stream = None
-        self._step = 0
+        self._gather_stream = None
+        self._gather_group = None               # step(): the mosaic gather runs on its own communicator + stream, so that the
+        self._step = 0                          # gather of scene k overlaps the halo exchange of scene k+1
         W = spec.width
         # only the planes the channels are derived from travel (config 3: count, sum_z, max_i = 3 of 6)
         self.planes = list(self.backend.planes(spec)) if self.need_acc else []
@@ -201,9 +203,12 @@ class StripRasterizer:
         strip = out["image"][p.top:hl - p.bottom]
         ready = torch.cuda.Event(enable_timing=self.time_stages)
         ready.record(main)
+        if self._gather_stream is None:
+            self._gather_stream = torch.cuda.Stream(self.device)
+            if self.world > 1 and self.gather_root != "none":
+                self._gather_group = dist.new_group(ranks=None if self.group is None else dist.get_process_group_ranks(self.group))
         with torch.cuda.stream(self._comm_stream):
-            # everything after the local rasterisation -- halo exchange, merge, re-finish of the edge
-            # bands, mosaic gather -- runs on the side stream, under the next scene's rasterisation
+            # after the local rasterisation: halo exchange, merge + re-finish of the edge bands on one side stream ...
             self._comm_stream.wait_event(ready)
             if ev:
                 ev[1].record(self._comm_stream)
@@ -211,11 +216,23 @@ class StripRasterizer:
                 self._exchange_and_merge(out, ev[2:3] if ev else None)
             elif ev:
                 ev[2].record(self._comm_stream)
-            if ev:
-                ev[3].record(self._comm_stream)
-            self._mosaics[k] = self.gather(strip, self.gather_root) if self.gather_root != "none" else None
+            merged = torch.cuda.Event(enable_timing=self.time_stages)
+            merged.record(self._comm_stream)
+        with torch.cuda.stream(self._gather_stream):
+            # ... and the mosaic gather on another one with its own communicator: all of it under the next scenes' rasterisation
+            self._gather_stream.wait_event(merged)
+            if self.gather_root != "none":
+                grp, self.group = self.group, (self._gather_group if self._gather_group is not None else self.group)
+                try:
+                    self._mosaics[k] = self.gather(strip, self.gather_root)
+                finally:
+                    self.group = grp
+            else:
+                self._mosaics[k] = None
             done = torch.cuda.Event(enable_timing=self.time_stages)
-            done.record(self._comm_stream)
+            done.record(self._gather_stream)
+        if ev:
+            ev[3] = merged
         if ev:
             self._stage_events.append((ev[0], ready, ev[1], ev[2], ev[3], done))
             del self._stage_events[:-64]
@@ -278,6 +295,13 @@ class StripRasterizer:
                 finalize_rows(self.local_spec, acc, band.start, band.stop, {"image": o["image"]})
         want = o["image"][p.top:hl - p.bottom]
         return int((want != strip).sum().item())
+
+    def close(self) -> None:
+        """Destroy the gather communicator (before ``dist.destroy_process_group``)."""
+        if self._gather_group is not None:
+            torch.cuda.synchronize(self.device)
+            dist.destroy_process_group(self._gather_group)
+            self._gather_group = None
 
     def mosaic(self, slot: int) -> Optional[torch.Tensor]:
         """The scene's mosaic (None on the ranks a rooted gather leaves empty); the current stream waits
