@@ -87,6 +87,7 @@ constexpr int RED_THREADS = 512;
 constexpr int RED_MIN_CTAS = 2;          // shared-memory tiles are sized so that two CTAs fit per SM
 constexpr int MAX_TILES = 15000;          // bin_points keeps 4 * (1 + NSLOT) B of append state per tile in shared memory
 constexpr uint32_t INVALID_U32 = 0xFFFFFFFFu;
+constexpr long long SCAN_IN_BIN_MAX_POINTS = 32ll << 20;   // calls up to this size fold scan_tiles into bin_points' last CTA
 
 // accumulator planes held in shared memory by reduce_tiles (bit mask)
 enum : int { M_CNT = 1, M_SUMI = 2, M_SUMZ = 4, M_MAXI = 8, M_MINZ = 16, M_MAXZ = 32, M_ALL = 63 };
@@ -120,7 +121,8 @@ struct Ctl {                 // lives right after lm_bev_stats in the workspace;
     unsigned int tile_counter;  // reduce_tiles scheduler
     unsigned int sweep_fail;    // LM_ALGO_SWEEP: != 0 -> the two-pass kernels behind the sweep do the raster
     unsigned int next_batch;    // sweep: batch counter of the producers
-    unsigned int pad[4];
+    unsigned int bin_done;      // bin_points CTAs that have retired (the last one builds the tile tables)
+    unsigned int pad[3];
 };
 
 struct Ws {                  // device pointers into the caller's workspace
@@ -138,6 +140,9 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t pool_chunks;    // P
     uint32_t region;         // chunks per bin CTA: CTA b owns chunk ids [b * region, (b + 1) * region), local id 0 = none
     uint32_t bin_grid;       // bin CTAs of this launch
+    uint32_t scan_in_bin = 0;   // 1: the last bin_points CTA builds the tile tables (no scan_tiles launch: small, launch-bound
+                                // calls); 0: scan_tiles_kernel does (large calls: the serial tail behind a 0.35 ms kernel and the
+                                // fences of 592 CTAs cost more than the launch, measured +4 us on config 2)
     const unsigned int *gate = nullptr;   // non-NULL: the kernels of the two-pass path return at once unless *gate != 0
                                 // (they sit behind a sweep, lm_sweep.cuh, and only run when it gave up)
 };
@@ -442,6 +447,76 @@ struct BatchTab {
     int nb, bH;
 };
 
+// ------------------------------------------------------------------------------------------
+// per-tile tables: first index of every tile's piece list + heaviest-first tile order.  Runs in the LAST
+// bin_points CTA to retire (no launch of its own), or as scan_tiles_kernel when no bin kernel ran.
+// scratch: NT + 1024 + 8 words of shared memory.
+// ------------------------------------------------------------------------------------------
+// inclusive block scan of one value per thread: warp shuffles + one pass over the warp totals (3 barriers)
+template <int NT>
+__device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t *s_warp /* [NT / 32] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    __syncthreads();                       // s_warp may still be read from a previous scan
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) base += w < warp ? s_warp[w] : 0u;
+    return v + base;
+}
+
+template <int NT>
+__device__ __forceinline__ void scan_tiles_body(const Ws &ws, const KParams &kp, uint32_t *scratch) {
+    const int T = kp.T;
+    uint32_t *s_lvl = scratch;              // [1024] tiles per weight level -> end of every level's slot range
+    uint32_t *s_warp = scratch + 1024;      // [NT / 32]
+    uint32_t *s_flag = s_warp + NT / 32;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_flag[0] = ws.stats->error & LM_DEV_ERR_POOL;
+        ws.stats->n_tiles = (uint32_t)T;
+    }
+    for (int i = tid; i < 1024; i += NT) s_lvl[i] = 0;
+    __syncthreads();
+    const int per = (T + NT - 1) / NT;
+    const int lo = tid * per, hi = min(T, lo + per);
+    if (s_flag[0]) {   // pool exhausted: publish an empty raster instead of reading half-built lists
+        for (int t = lo; t < hi; ++t) ws.tile_nchunks[t] = 0;
+    }
+    uint32_t sum = 0;
+    for (int t = lo; t < hi; ++t) {
+        const uint32_t c = __ldcg(&ws.tile_nchunks[t]);      // other CTAs' atomics: read at the L2
+        sum += c;
+        atomicAdd(&s_lvl[1023u - min(c, 1023u)], 1u);      // level 0 = heaviest
+    }
+    uint32_t run = block_inclusive_scan<NT>(sum, s_warp) - sum;      // first piece index of this thread's tiles
+    // inclusive scan of the 1024 level counts: 1024 / NT consecutive levels per thread, then across threads
+    constexpr int LPT = 1024 / NT;
+    uint32_t lsum = 0;
+#pragma unroll
+    for (int q = 0; q < LPT; ++q) { lsum += s_lvl[tid * LPT + q]; s_lvl[tid * LPT + q] = lsum; }
+    const uint32_t lbase = block_inclusive_scan<NT>(lsum, s_warp) - lsum;
+#pragma unroll
+    for (int q = 0; q < LPT; ++q) s_lvl[tid * LPT + q] += lbase;
+    __syncthreads();
+    for (int t = lo; t < hi; ++t) {
+        ws.tile_first[t] = run;
+        run += __ldcg(&ws.tile_nchunks[t]);
+    }
+    // counting sort by weight level: tile_order lists the heaviest tiles first so that the persistent
+    // reduce CTAs finish together (longest-processing-time-first)
+    for (int t = lo; t < hi; ++t) {
+        const uint32_t lvl = 1023u - min(__ldcg(&ws.tile_nchunks[t]), 1023u);
+        const uint32_t pos = atomicAdd(&s_lvl[lvl], 0xFFFFFFFFu) - 1u;      // fill each level's slot range from its end
+        ws.tile_order[pos] = (uint32_t)t;
+    }
+}
+
 // LAS: the input is the point-data block of an uncompressed LAS file (record_length bytes per point)
 // and the decode of lm_dev.cuh::las_decode_record runs on the staged bytes; no float4 copy of the
 // cloud ever exists in HBM.
@@ -676,6 +751,19 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         ws.cta_chunks[blockIdx.x] = used;
         if (used) atomicAdd(&ws.stats->n_chunks, used);
     }
+    // ---- the last CTA to retire has every tile's piece count in front of it: it builds the tile tables
+    //      (what used to be the scan_tiles launch), in the stage buffers nobody needs any more
+    if (!ws.scan_in_bin) return;
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&ws.ctl->bin_done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        static_assert(BIN_STAGES * BIN_BATCH * 16 >= (1024 + BIN_THREADS / 32 + 8) * 4, "scan scratch fits the stage buffers");
+        scan_tiles_body<BIN_THREADS>(ws, kp, reinterpret_cast<uint32_t *>(smem_raw));
+    }
 }
 
 
@@ -753,50 +841,8 @@ __device__ __forceinline__ bool tile_in_band(const KParams &kp, int t) {
 
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
     if (gated_off(ws)) return;
-    const int T = kp.T;
-    __shared__ uint32_t s_part[1024];
-    __shared__ uint32_t s_lvl[1024];
-    __shared__ uint32_t s_err;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        s_err = ws.stats->error & LM_DEV_ERR_POOL;
-        ws.stats->n_tiles = (uint32_t)T;
-    }
-    s_lvl[tid] = 0;
-    __syncthreads();
-    const int per = (T + 1023) / 1024;
-    const int lo = tid * per, hi = min(T, lo + per);
-    if (s_err) {   // pool exhausted: publish an empty raster instead of reading half-built lists
-        for (int t = lo; t < hi; ++t) ws.tile_nchunks[t] = 0;
-    }
-    uint32_t sum = 0;
-    for (int t = lo; t < hi; ++t) {
-        const uint32_t c = ws.tile_nchunks[t];
-        sum += c;
-        atomicAdd(&s_lvl[1023u - min(c, 1023u)], 1u);      // level 0 = heaviest
-    }
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scans (chunk offsets, level offsets)
-        const uint32_t v = tid >= o ? s_part[tid - o] : 0u;
-        const uint32_t w = tid >= o ? s_lvl[tid - o] : 0u;
-        __syncthreads();
-        s_part[tid] += v;
-        s_lvl[tid] += w;
-        __syncthreads();
-    }
-    uint32_t run = s_part[tid] - sum;
-    for (int t = lo; t < hi; ++t) {
-        ws.tile_first[t] = run;
-        run += ws.tile_nchunks[t];
-    }
-    // counting sort by weight level: tile_order lists the heaviest tiles first so that the persistent
-    // reduce CTAs finish together (longest-processing-time-first)
-    for (int t = lo; t < hi; ++t) {
-        const uint32_t lvl = 1023u - min(ws.tile_nchunks[t], 1023u);
-        const uint32_t pos = atomicAdd(&s_lvl[lvl], 0xFFFFFFFFu) - 1u;      // fill each level's slot range from its end
-        ws.tile_order[pos] = (uint32_t)t;
-    }
+    __shared__ uint32_t s_scratch[1024 + 32 + 8];
+    scan_tiles_body<1024>(ws, kp, s_scratch);
 }
 
 __global__ void index_chunks_kernel(Ws ws) {
@@ -1665,6 +1711,7 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
         int grid = 0;
         ws.region = 1;
         ws.bin_grid = 0;
+        ws.scan_in_bin = n_points > 0 && n_points <= SCAN_IN_BIN_MAX_POINTS;
         if (n_points > 0) {
             rc = bin_geometry(las ? (const void *)bin_points_las_kernel : (const void *)bin_points_kernel, smem, nb, kp.T, kp.tiles_x, sms, L, &ws, &grid);
             if (rc) return rc;
@@ -1689,8 +1736,8 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
             else if (n_points > 0)
                 bin_points_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, ws);
         }
-        if (stages & LM_STAGE_INDEX) {
-            scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
+        if (stages & LM_STAGE_INDEX) {      // (small calls: the tile tables were built by the last bin CTA)
+            if (!ws.scan_in_bin) scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
             if (n_points > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
         }
         e = cudaGetLastError();
@@ -1893,6 +1940,7 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
         if (e != cudaSuccess) return cuda_fail(e, "memset");
         ws.region = 1;
         ws.bin_grid = 0;
+        ws.scan_in_bin = batches > 0 && gpts <= SCAN_IN_BIN_MAX_POINTS;
         if (batches > 0) {
             const size_t smem = bin_smem_bytes(kp.T);
             int grid = 0;
@@ -1900,7 +1948,7 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
             if (rc) return rc;
             bin_points_batch_kernel<<<grid, BIN_THREADS, smem, st>>>(kp, bt, ws);
         }
-        scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
+        if (!ws.scan_in_bin) scan_tiles_kernel<<<1, 1024, 0, st>>>(ws, kp);
         if (batches > 0) index_chunks_kernel<<<sms * 4, 256, 0, st>>>(ws);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "bin/index launch");
