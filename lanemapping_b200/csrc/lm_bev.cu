@@ -1562,27 +1562,32 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
     if (rc) return rc;
     if (!bytes || n_points < 0) return fail(LM_ERR_INVALID, "bytes is NULL or n_points < 0");
     if (algo != LM_ALGO_BINNED && algo != LM_ALGO_DIRECT && algo != LM_ALGO_SWEEP) return fail(LM_ERR_INVALID, "unknown algo %d", algo);
-    // the tile height depends on the accumulator planes the outputs need; without an output set
-    // size for the smallest tiles (raw accumulators) so that any call fits
-    int th = 5;
+    // the tile height depends on the accumulator planes the outputs need.  Without an output set the bound has to
+    // hold for every one: the pool reserves bin_ctas_bound(T) * (T + 2) chunks, which is NOT monotonic in the tile
+    // count T (the CTAs per SM drop as T grows), so take the maximum over the three tile heights
+    int th_lo = 5, th_hi = 7;
     if (out) {
         const bool want16 = out->count16_dev != nullptr;
         const bool banded = out->acc_dev != nullptr && out->acc_band > 0 &&
                             (out->image_dev || out->count16_dev || out->proj_dev);
-        th = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16), p->height, p->width);
+        th_lo = th_hi = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16), p->height, p->width);
     }
-    KParams k = make_kparams(p, th);
-    if (algo != LM_ALGO_DIRECT) {          // a raster with too many tiles runs as row windows: size for one window
-        const int wrows = window_rows(p, th);
-        if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: %d tiles per tile row > %d", k.tiles_x, max_tiles());
-        lm_bev_params pw = *p;
-        pw.height = wrows;
-        k = make_kparams(&pw, th);
+    size_t best = 0;
+    for (int th = th_lo; th <= th_hi; ++th) {
+        KParams k = make_kparams(p, th);
+        if (algo != LM_ALGO_DIRECT) {          // a raster with too many tiles runs as row windows: size for one window
+            const int wrows = window_rows(p, th);
+            if (wrows == 0) return fail(LM_ERR_UNSUPPORTED, "raster too wide: %d tiles per tile row > %d", k.tiles_x, max_tiles());
+            lm_bev_params pw = *p;
+            pw.height = wrows;
+            k = make_kparams(&pw, th);
+        }
+        Layout L;
+        rc = make_layout(p, n_points, algo, k.T, &L);
+        if (rc) return rc;
+        if (L.total > best) best = L.total;
     }
-    Layout L;
-    rc = make_layout(p, n_points, algo, k.T, &L);
-    if (rc) return rc;
-    *bytes = L.total;
+    *bytes = best;
     return LM_OK;
 }
 
@@ -1850,12 +1855,20 @@ int lm_bev_workspace_bytes_batch(const lm_bev_params *p, int32_t n_samples, int6
     }
     const int g = batch_group(p, th, n_samples);
     if (g < 1) return lm_bev_workspace_bytes(p, n_points_total, LM_ALGO_BINNED, out, bytes);
-    lm_bev_params ps = *p;
-    ps.height = p->height * g;
-    Layout L;
-    rc = make_layout(&ps, n_points_total, LM_ALGO_BINNED, make_kparams(&ps, th).T, &L);
-    if (rc) return rc;
-    *bytes = L.total;
+    // the call runs launch sets of g samples and one last set of n_samples % g: the smaller set has fewer tiles, may
+    // therefore run more bin CTAs per SM and reserve a LARGER pool -- size for both
+    size_t best = 0;
+    const int sets[2] = {g, n_samples % g};
+    for (int k = 0; k < 2; ++k) {
+        if (sets[k] < 1) continue;
+        lm_bev_params ps = *p;
+        ps.height = p->height * sets[k];
+        Layout L;
+        rc = make_layout(&ps, n_points_total, LM_ALGO_BINNED, make_kparams(&ps, th).T, &L);
+        if (rc) return rc;
+        if (L.total > best) best = L.total;
+    }
+    *bytes = best;
     return LM_OK;
 }
 
