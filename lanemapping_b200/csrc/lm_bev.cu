@@ -30,7 +30,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <new>
+#include <vector>
 
 namespace {
 extern thread_local char g_err[512];
@@ -1337,6 +1339,39 @@ KParams make_kparams(const lm_bev_params *p, int tile_h_log2) {
     return k;
 }
 
+// cudaFuncSetAttribute + cudaOccupancyMaxActiveBlocksPerMultiprocessor cost microseconds of HOST time per call -- what
+// bounds the small configs when no graph is replayed.  Their results depend on (kernel, block size, dynamic shared
+// memory, device) only, so they are memoised per process (a cache of pure function results, guarded by a mutex; the
+// attribute is raised once per kernel and device to the largest size asked for so far).
+struct OccEntry { const void *kernel; size_t smem; int threads, device, occ; };
+int cached_occupancy(const void *kernel, int threads, size_t smem, int *occ_out) {
+    static std::mutex mu;
+    static std::vector<OccEntry> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    size_t attr_set = 0;
+    for (const OccEntry &e : cache) {
+        if (e.kernel == kernel && e.device == dev) {
+            if (e.smem > attr_set) attr_set = e.smem;
+            if (e.smem == smem && e.threads == threads) { *occ_out = e.occ; return LM_OK; }
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (smem > attr_set) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "shared-memory attribute");
+        // the same (maximal) carve-out for every kernel of the pipeline: an SM only switches its L1/shared split when idle
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    }
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy query");
+    cache.push_back(OccEntry{kernel, smem, threads, dev, occ});
+    *occ_out = occ;
+    return LM_OK;
+}
+
 size_t bin_smem_bytes(int T) { return BIN_STAGES * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * (4 + 2 * NSLOT); }
 
 // chunks per bin CTA when `grid` CTAs share `nb` batches: the chunks its points can fill, one open
@@ -1461,12 +1496,8 @@ SweepWs make_sweep_ws(unsigned char *w, size_t workspace_bytes, Ctl *ctl) {
 template <int MASK>
 cudaError_t launch_sweep(const KParams &kp, const float4 *pts, long long n, const SweepWs &sw, const Outs &o, int sms, bool *fits,
                          bool launch, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(sweep_kernel<MASK>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<MASK>, SW_THREADS, SW_SMEM);
-    if (e != cudaSuccess) return e;
+    if (cached_occupancy(reinterpret_cast<const void *>(sweep_kernel<MASK>), SW_THREADS, SW_SMEM, &occ)) return cudaErrorUnknown;
     *fits = (long long)occ * sms >= SW_GRID;
     if (!*fits || !launch) return cudaSuccess;
     sweep_kernel<MASK><<<SW_GRID, SW_THREADS, SW_SMEM, st>>>(kp, pts, n, sw, o);
@@ -1485,14 +1516,8 @@ cudaError_t launch_sweep_mask(int mask, const KParams &kp, const float4 *pts, lo
 // persistent, one wave of resident CTAs, each owning a contiguous range of the nb batches.
 int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles_x, int sms, const Layout &L, Ws *ws, int *grid_out) {
     if (smem > 220 * 1024) return fail(LM_ERR_UNSUPPORTED, "%zu bytes of shared memory per bin CTA: too many tiles / too long records", smem);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "bin_points smem attribute");
-    // the same (maximal) shared-memory carve-out for every kernel of the pipeline: an SM only switches its L1/shared
-    // split when idle, so kernels with different carve-outs never share an SM (no bin/reduce overlap)
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BIN_THREADS, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "bin_points occupancy");
+    if (int rc = cached_occupancy(kernel, BIN_THREADS, smem, &occ)) return rc;
     // A raster wider than four crops is a multi-road scene: the scan visits one road at a time and its
     // stray returns spread over every tile column, so every (CTA, tile) pair keeps a slowly filling open
     // chunk.  Fewer, faster-moving CTAs fill those sectors sooner: 3 per SM measured best on the
@@ -1520,12 +1545,8 @@ int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles
 template <int MASK>
 cudaError_t launch_reduce(const KParams &kp, const Ws &ws, const Outs &o, int sms, cudaStream_t st) {
     const size_t smem = (size_t)popc6(MASK) * ((size_t)TILE_W << kp.tile_h_log2) * 4;
-    cudaError_t e = cudaFuncSetAttribute(reduce_tiles_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(reduce_tiles_kernel<MASK>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tiles_kernel<MASK>, RED_THREADS, smem);
-    if (e != cudaSuccess) return e;
+    if (cached_occupancy(reinterpret_cast<const void *>(reduce_tiles_kernel<MASK>), RED_THREADS, smem, &occ)) return cudaErrorUnknown;
     if (occ < 1) occ = 1;
     if (const int v = g_tune->red_ctas_per_sm) {                  // tuning knob
         if (v >= 1 && v < occ) occ = v;

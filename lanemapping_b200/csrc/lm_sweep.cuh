@@ -243,7 +243,7 @@ __device__ __forceinline__ void sweep_producer(const KParams &kp, const float4 *
 
     int m_last = 0;
     bool have_marker = false, panic = false;
-    unsigned long long d_rounds = 0, d_markers = 0, d_batches = 0, d_wait = 0, d_tma = 0;
+    [[maybe_unused]] unsigned long long d_rounds = 0, d_markers = 0, d_batches = 0, d_wait = 0, d_tma = 0;
     for (int k = 0;; ++k) {
         const uint32_t buf = (uint32_t)k % (uint32_t)SW_STAGES;
         const int cur = s_misc[5 + buf];
@@ -520,7 +520,7 @@ __device__ __forceinline__ void sweep_consumer(const KParams &kp, const SweepWs 
     };
 
     const unsigned long long t_start = sweep_now_ns();
-    unsigned long long d_polls = 0, d_hits = 0, d_gated = 0, d_emit = 0;
+    [[maybe_unused]] unsigned long long d_polls = 0, d_hits = 0, d_gated = 0, d_emit = 0;
     // the granule at every mailbox's head is fetched one loop ahead (registers): the L2 round trip of mailbox i
     // runs under the reduction of the other mailboxes' granules and the frontier bookkeeping
     uint4 glo[SW_MBPT], ghi[SW_MBPT];

@@ -111,3 +111,50 @@ def test_batch_and_las_argument_errors(native_lib):
     assert native_lib.lm_las_decode(None, 0, C.byref(x), None, None) == 0          # nothing to do
     assert native_lib.lm_las_decode(None, 5, C.byref(x), None, None) == -1
     assert native_lib.lm_las_decode(None, 0, None, None, None) == -1
+
+
+def test_plan_api_without_a_gpu(native_lib):
+    """lm_bev_plan_*: creation, sizing and argument errors need no device; the tuning knobs are plan fields (the
+    library reads no environment variables) and the workspace bound without an output set covers every output set."""
+    spec = BevSpec(2304, 1152)
+    p = _cabi.make_params(spec)
+    o = _cabi.LmBevOutputs()
+    o.image_dev = 1
+    plan = C.c_void_p()
+    assert native_lib.lm_bev_plan_create(C.byref(p), 1_000_000, _cabi.ALGO_BINNED, None, None, C.byref(plan)) == -1   # no output set
+    assert native_lib.lm_bev_plan_create(C.byref(p), 1_000_000, 9, C.byref(o), None, C.byref(plan)) == -1           # unknown algo
+    assert native_lib.lm_bev_plan_create(C.byref(p), 1_000_000, _cabi.ALGO_BINNED, C.byref(o), None, C.byref(plan)) == 0
+    nbytes, legacy = C.c_size_t(0), C.c_size_t(0)
+    assert native_lib.lm_bev_plan_workspace_bytes(plan, C.byref(nbytes)) == 0
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 1_000_000, _cabi.ALGO_BINNED, C.byref(o), C.byref(legacy)) == 0
+    assert nbytes.value == legacy.value and nbytes.value % 256 == 0
+    assert native_lib.lm_bev_plan_rasterize(plan, None, 2_000_000, None, 0, C.byref(o), None) == -1                 # > max_points
+    assert native_lib.lm_bev_plan_rasterize(plan, None, 0, None, 0, C.byref(o), None) == -2                         # no workspace
+    assert native_lib.lm_bev_plan_destroy(plan) == 0 and native_lib.lm_bev_plan_destroy(None) == 0
+    # a tuning field changes the layout the plan sizes for: fewer tiles per launch -> a smaller pool reservation
+    t = _cabi.LmBevTuning()
+    t.max_tiles = 9
+    plan2 = C.c_void_p()
+    assert native_lib.lm_bev_plan_create(C.byref(p), 1_000_000, _cabi.ALGO_BINNED, C.byref(o), C.byref(t), C.byref(plan2)) == 0
+    small = C.c_size_t(0)
+    assert native_lib.lm_bev_plan_workspace_bytes(plan2, C.byref(small)) == 0 and small.value < nbytes.value
+    native_lib.lm_bev_plan_destroy(plan2)
+    # the sweep algorithm reserves its mailboxes at the END of the workspace
+    sw = C.c_size_t(0)
+    assert native_lib.lm_bev_workspace_bytes(C.byref(p), 1_000_000, _cabi.ALGO_SWEEP, C.byref(o), C.byref(sw)) == 0
+    off = C.c_size_t(0)
+    assert native_lib.lm_bev_sweep_state_offset(sw.value, C.byref(off)) == 0
+    assert legacy.value <= off.value < sw.value and sw.value - off.value > 296 * 148 * 8 * 32
+    assert native_lib.lm_bev_sweep_state_offset(1000, C.byref(off)) == -1
+    # the bound without an output set holds for every output set (advisor, round 1): try the three tile heights
+    bound = C.c_size_t(0)
+    for h, w in ((2304, 1152), (28800, 3456), (1440, 11520), (700, 300)):
+        pp = _cabi.make_params(BevSpec(h, w, count16=True))
+        assert native_lib.lm_bev_workspace_bytes(C.byref(pp), 5_000_000, _cabi.ALGO_BINNED, None, C.byref(bound)) == 0
+        for outs in (("image",), ("image", "count16"), ("acc",), ("proj", "acc")):
+            oo = _cabi.LmBevOutputs()
+            for k in outs:
+                setattr(oo, k + "_dev", 1)
+            need = C.c_size_t(0)
+            assert native_lib.lm_bev_workspace_bytes(C.byref(pp), 5_000_000, _cabi.ALGO_BINNED, C.byref(oo), C.byref(need)) == 0
+            assert need.value <= bound.value, (h, w, outs)
