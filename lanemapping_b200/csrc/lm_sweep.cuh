@@ -122,10 +122,10 @@ __device__ __forceinline__ void reds_max(uint32_t a, uint32_t v) {
 }
 // predicated forms: ONE instruction under a predicate, never a branch around it
 __device__ __forceinline__ void reds_add_if(bool p, uint32_t a, uint32_t v) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q red.shared.add.u32 [%1], %2;\n}" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q red.shared.add.u32 [%1], %2;\n}" ::"r"((uint32_t)p), "r"(a), "r"(v));
 }
 __device__ __forceinline__ void reds_max_if(bool p, uint32_t a, uint32_t v) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q red.shared.max.u32 [%1], %2;\n}" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q red.shared.max.u32 [%1], %2;\n}" ::"r"((uint32_t)p), "r"(a), "r"(v));
 }
 
 __device__ __forceinline__ unsigned long long sweep_now_ns() {
@@ -581,7 +581,7 @@ __device__ __forceinline__ void sweep_consumer(const KParams &kp, const SweepWs 
                     const uint32_t slot = ((((x >> 16) & (SW_R - 1)) * SW_CPO) + ((x >> 27) & 7u)) * 4u;   // always inside the window
                     const uint32_t iqv = (x >> 8) & 0xFFu;
                     if (HAS_CNT) reds_add_if(take, sm_w0 + slot, (1u << PK_SHIFT) | (HAS_SUM ? (x & 0xFFu) : 0u));
-                    reds_max_if(take && iqv > lds_u32(sm_w1 + slot), sm_w1 + slot, iqv);
+                    reds_max_if(take, sm_w1 + slot, iqv);
                 }
                 n_valid += taken;
                 mark[i] = cm;
