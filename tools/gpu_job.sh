@@ -12,19 +12,8 @@ case "$JOB" in
     TAG=${1:-x}; shift || true
     timeout ${T:-600} python bench.py "$@" > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
     cut -c1-2500 gpurun_out/bench_$TAG.json; tail -n 3 gpurun_out/bench_$TAG.err ;;
-  overlap)      # two-stream scene pipelining, A/B over TMA stage count (needs csrc/liblm_bev_s{3,4}.so) and CTAs per SM
-    for LIB in liblm_bev.so liblm_bev_s3.so liblm_bev_s4.so; do
-      [ -f lanemapping_b200/csrc/$LIB ] || continue
-      for BC in 2 3; do
-        echo "== $LIB bin_ctas/SM=$BC red_ctas/SM=1"
-        LM_BEV_LIB=$LIB LM_BEV_BIN_CTAS_PER_SM=$BC LM_BEV_RED_CTAS_PER_SM=1 timeout 300 python bench.py --overlap --no-cpu-baseline \
-            --steps 20 --warmup 3 --e2e-steps 1 2> gpurun_out/overlap.err | python -c "
-import sys, json
-d = json.loads(sys.stdin.readline())
-print(d['ms_per_step'], d['value'], d.get('roofline', {}).get('stage_ms'), d.get('roofline', {}).get('path_frac'))"
-      done
-    done 2>&1 | tee gpurun_out/overlap_sweep.txt ;;
   l2ring)       # tools/l2ring: does a recycled record ring stay in L2 under the point stream? (timing + DRAM bytes)
+    [ -x tools/l2ring ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/l2ring tools/l2ring.cu
     for R in 8 16 32 64; do for P in 0 1 2 3; do ./tools/l2ring $R 0.5 $P | grep "^ring"; done; done | tee gpurun_out/l2ring_time.txt
     ./tools/l2ring 32 0.5 0 | grep -v "^ring" | tee -a gpurun_out/l2ring_time.txt
     [ "${NCU:-1}" = 1 ] || exit 0
@@ -43,5 +32,5 @@ print(d['ms_per_step'], d['value'], d.get('roofline', {}).get('stage_ms'), d.get
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 "$@" > gpurun_out/launches_$TAG.log 2>&1
     tail -n 40 gpurun_out/launches_$TAG.csv | cut -c1-220 ;;
-  *) echo "jobs: tests | bench | overlap | l2ring | ncu | launches"; exit 2 ;;
+  *) echo "jobs: tests | bench | l2ring | ncu | launches"; exit 2 ;;
 esac
