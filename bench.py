@@ -454,7 +454,8 @@ def run_ours(args):
     else:
         from lanemapping_b200.strips import StripRasterizer
         groot = {"root": 0, "all": None, "none": "none"}[args.gather]
-        sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev, align=STRIP_ALIGN, gather_root=groot, time_stages=True)
+        sr = StripRasterizer(spec, n_pts, halo=args.halo, device=dev, align=STRIP_ALIGN, gather_root=groot, time_stages=True,
+                             gather_parts=args.gather_parts)
         mosaic_holder = {}
 
         def step():
@@ -693,6 +694,8 @@ def main():
                     help="N > 1: halo rows per side (the scan jitter of the synthetic clouds strays <= 20 rows)")
     ap.add_argument("--gather", default="root", choices=["root", "all", "none"],
                     help="N > 1: assemble the mosaic on rank 0 (gather), on every rank (all-gather), or leave it sharded")
+    ap.add_argument("--gather-parts", type=int, default=1,
+                    help="N > 1, --gather root: split the gather into this many row blocks on separate communicators")
     ap.add_argument("--cpu-points", type=int, default=0,
                     help="points of the CPU sample (0: the full config for --impl reference, 20 M for the in-line cpu_baseline)")
     ap.add_argument("--e2e-steps", type=int, default=5)

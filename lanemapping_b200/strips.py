@@ -109,13 +109,14 @@ class StripRasterizer:
 
     def __init__(self, spec: BevSpec, max_points: int, halo: int = 64, group=None, backend=None,
                  device: Optional[torch.device | str] = None, align: int = 128, gather_root=None,
-                 time_stages: bool = False):
+                 time_stages: bool = False, gather_parts: int = 1):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.spec = spec
         self.gather_root = gather_root          # step(): None = mosaic on every rank, r = on rank r only, "none" = stays sharded
         self.time_stages = time_stages          # step(): record events around the stages (stage_times())
+        self.gather_parts = max(1, int(gather_parts))   # step(): rooted gather split into row blocks on separate communicators
         self.plan = make_plan(spec, self.rank, self.world, halo, align)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.backend = backend if backend is not None else CudaBackend(self.device)
@@ -135,6 +136,7 @@ class StripRasterizer:
         self._gather_stream = None
         self._gather_group = None               # step(): the mosaic gather runs on its own communicator + stream, so that the
         self._step = 0                          # gather of scene k overlaps the halo exchange of scene k+1
+        self._part_groups, self._part_streams = [], []
         W = spec.width
         # only the planes the channels are derived from travel (config 3: count, sum_z, max_i = 3 of 6)
         self.planes = list(self.backend.planes(spec)) if self.need_acc else []
@@ -206,7 +208,14 @@ class StripRasterizer:
         if self._gather_stream is None:
             self._gather_stream = torch.cuda.Stream(self.device)
             if self.world > 1 and self.gather_root != "none":
-                self._gather_group = dist.new_group(ranks=None if self.group is None else dist.get_process_group_ranks(self.group))
+                ranks = None if self.group is None else dist.get_process_group_ranks(self.group)
+                self._gather_group = dist.new_group(ranks=ranks)
+                rows = [b - a for a, b in self.plan.bounds]
+                if self.gather_parts > 1 and isinstance(self.gather_root, int) and all(r == rows[0] for r in rows):
+                    # NCCL's send/recv fan-in runs on a few CTAs per communicator: several communicators, each moving one
+                    # row block of every strip on its own stream, put more of them on the links
+                    self._part_groups = [self._gather_group] + [dist.new_group(ranks=ranks) for _ in range(self.gather_parts - 1)]
+                    self._part_streams = [self._gather_stream] + [torch.cuda.Stream(self.device) for _ in range(self.gather_parts - 1)]
         with torch.cuda.stream(self._comm_stream):
             # after the local rasterisation: halo exchange, merge + re-finish of the edge bands on one side stream ...
             self._comm_stream.wait_event(ready)
@@ -221,14 +230,16 @@ class StripRasterizer:
         with torch.cuda.stream(self._gather_stream):
             # ... and the mosaic gather on another one with its own communicator: all of it under the next scenes' rasterisation
             self._gather_stream.wait_event(merged)
-            if self.gather_root != "none":
+            if self.gather_root == "none":
+                self._mosaics[k] = None
+            elif self._part_groups:
+                self._mosaics[k] = self._gather_in_parts(strip, merged)
+            else:
                 grp, self.group = self.group, (self._gather_group if self._gather_group is not None else self.group)
                 try:
                     self._mosaics[k] = self.gather(strip, self.gather_root)
                 finally:
                     self.group = grp
-            else:
-                self._mosaics[k] = None
             done = torch.cuda.Event(enable_timing=self.time_stages)
             done.record(self._gather_stream)
         if ev:
@@ -295,6 +306,34 @@ class StripRasterizer:
                 finalize_rows(self.local_spec, acc, band.start, band.stop, {"image": o["image"]})
         want = o["image"][p.top:hl - p.bottom]
         return int((want != strip).sum().item())
+
+    def _gather_in_parts(self, strip: torch.Tensor, merged) -> Optional[torch.Tensor]:
+        """Rooted gather of equal strips as ``gather_parts`` row blocks, one communicator + stream each (called on the
+        first gather stream, which then waits for the others)."""
+        root, P = self.gather_root, len(self._part_groups)
+        is_root = self.rank == root
+        rows = strip.shape[0]
+        W, C = strip.shape[1], strip.shape[2]
+        mosaic = torch.empty((self.spec.height, W, C), dtype=strip.dtype, device=strip.device) if is_root else None
+        cuts = [rows * q // P for q in range(P + 1)]
+        evs = []
+        for q in range(P):
+            st = self._part_streams[q]
+            if q:
+                st.wait_event(merged)
+                if mosaic is not None:
+                    mosaic.record_stream(st)
+            with torch.cuda.stream(st):
+                a, b = cuts[q], cuts[q + 1]
+                parts = [mosaic[r * rows + a:r * rows + b] for r in range(self.world)] if is_root else None
+                dist.gather(strip[a:b], parts, dst=self._peer(root), group=self._part_groups[q])
+                if q:
+                    e = torch.cuda.Event()
+                    e.record(st)
+                    evs.append(e)
+        for e in evs:
+            self._gather_stream.wait_event(e)
+        return mosaic
 
     def close(self) -> None:
         """Destroy the gather communicator (before ``dist.destroy_process_group``)."""
