@@ -8,8 +8,9 @@ A *step* is one pass of the hot path over one synthetic cloud.
   N = 1   BASELINE.json configs[1]: 100 M-point road segment -> 11520 x 1152 x 3 u8 at 0.05 m.
   N > 1   configs[2] geometry, weak scaling: every rank owns one 1440-row strip of an
           (1440 N) x 11520 scene with 1.25e8 points (N = 8 is exactly the 1 B-point scene);
-          the step includes the NCCL halo merge and the mosaic gather on rank 0 (--gather all: all-gather
-          on every rank); the exchange and the gather of scene k run on a side stream under the
+          the step includes the NCCL halo exchange + merge; the finished mosaic stays sharded, one strip per GPU, and
+          every rank delivers its own strip in the e2e leg (--gather root / all: also gather it on rank 0 / on every
+          rank inside the step, and D2H it there); exchange, merge and gather of scene k run on side streams under the
           rasterisation of scene k+1 and all of them finish inside the timed region.
 ``value``  device-resident throughput (inputs in HBM when the clock starts), CUDA events,
            max over ranks.   ``e2e``: the same metric through the host-buffer API
@@ -66,7 +67,7 @@ def workload(n_gpus: int, rank: int, points_override: int = 0):
         sp = BevSpec(1440 * n_gpus, 11520, channels=ch)
         n = points_override or 125_000_000
         name = (f"configs[2] geometry, weak scaling: {n_gpus} strips of 1440x11520 cells @0.05 m, "
-                f"{n / 1e6:.0f}M points per GPU, halo merge + mosaic gather in the step")
+                f"{n / 1e6:.0f}M points per GPU, NCCL halo merge in the step")
     return replace(sp, local_min_ele=default_min_ele(BevSpec(1152, 1152))), n, name
 
 
@@ -692,8 +693,9 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="override points per GPU (debug)")
     ap.add_argument("--halo", type=int, default=32,
                     help="N > 1: halo rows per side (the scan jitter of the synthetic clouds strays <= 20 rows)")
-    ap.add_argument("--gather", default="root", choices=["root", "all", "none"],
-                    help="N > 1: assemble the mosaic on rank 0 (gather), on every rank (all-gather), or leave it sharded")
+    ap.add_argument("--gather", default="none", choices=["root", "all", "none"],
+                    help="N > 1: leave the finished mosaic sharded, one strip per GPU (default: every rank delivers / writes its own "
+                         "crops, as the multi-GPU offline converter does), or assemble it on rank 0 (root) / on every rank (all)")
     ap.add_argument("--gather-parts", type=int, default=1,
                     help="N > 1, --gather root: split the gather into this many row blocks on separate communicators")
     ap.add_argument("--cpu-points", type=int, default=0,
