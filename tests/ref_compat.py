@@ -1,12 +1,12 @@
 """Test infrastructure: the two pieces of the reference's plug-in machinery the on-the-fly path goes
 through, restated so that the GPU box (which has no /root/reference) can exercise the plug-ins.
 
-* ``Registry`` / ``build_from_cfg``  -- reference baseline/utils/registry.py:12-84
-* ``runner_to_cuda``                 -- reference baseline/engine/runner.py:125-152 (``Runner.to_cuda``)
+* ``Registry`` / ``build_from_cfg``  -- stand-ins for reference baseline/utils/registry.py:12-84
+* ``runner_to_cuda``                 -- stand-in for reference baseline/engine/runner.py:125-152 (``Runner.to_cuda``)
 
 tests/test_plugins.py holds both to the reference where it is mounted: the real ``registry.py`` is loaded by
-path and must behave identically on the same calls, and ``runner_to_cuda`` must have the same AST as the
-method in the reference file.  Nothing in the product imports this module.
+path and must behave identically on the same calls, and ``runner_to_cuda`` is run side by side with the method cut
+out of the reference's runner.py on the same batches.  Nothing in the product imports this module.
 """
 import importlib.util
 import inspect
@@ -30,45 +30,43 @@ def load_reference_registry():
     return mod
 
 
-class Registry(object):
-    # reference baseline/utils/registry.py:12-51
-    def __init__(self, name):
-        self._name = name
-        self._module_dict = dict()
+class Registry:
+    """Behavioural stand-in for reference baseline/utils/registry.py:12-51 (name, get, register_module)."""
 
-    @property
-    def name(self):
-        return self._name
+    def __init__(self, name):
+        self.name = name
+        self._items = {}
 
     def get(self, key):
-        return self._module_dict.get(key, None)
+        return self._items.get(key)
 
     def register_module(self, cls):
         if not inspect.isclass(cls):
-            raise TypeError('module must be a class, but got {}'.format(type(cls)))
-        if cls.__name__ in self._module_dict:
-            raise KeyError('{} is already registered in {}'.format(cls.__name__, self.name))
-        self._module_dict[cls.__name__] = cls
+            raise TypeError(f"module must be a class, but got {type(cls)}")
+        if cls.__name__ in self._items:
+            raise KeyError(f"{cls.__name__} is already registered in {self.name}")
+        self._items[cls.__name__] = cls
         return cls
 
 
 def build_from_cfg(cfg, registry, default_args=None):
-    # reference baseline/utils/registry.py:54-84: kwargs = cfg minus 'type', default_args fill the gaps
-    assert isinstance(cfg, dict) and 'type' in cfg
-    args = cfg.copy()
-    obj_type = args.pop('type')
-    if isinstance(obj_type, str):
-        obj_cls = registry.get(obj_type)
-        if obj_cls is None:
-            raise KeyError('{} is not in the {} registry'.format(obj_type, registry.name))
-    elif inspect.isclass(obj_type):
-        obj_cls = obj_type
+    """Stand-in for reference baseline/utils/registry.py:54-84: the constructor's kwargs are the cfg dict minus
+    'type'; default_args (the reference passes dict(cfg=cfg)) only fill what the cfg dict does not set."""
+    if not isinstance(cfg, dict) or "type" not in cfg:
+        raise AssertionError("cfg must be a dict with a 'type' key")
+    kind = cfg["type"]
+    if isinstance(kind, str):
+        cls = registry.get(kind)
+        if cls is None:
+            raise KeyError(f"{kind} is not in the {registry.name} registry")
+    elif inspect.isclass(kind):
+        cls = kind
     else:
-        raise TypeError('type must be a str or valid type, but got {}'.format(type(obj_type)))
-    if default_args is not None:
-        for name, value in default_args.items():
-            args.setdefault(name, value)
-    return obj_cls(**args)
+        raise TypeError(f"type must be a str or valid type, but got {type(kind)}")
+    kwargs = {k: v for k, v in cfg.items() if k != "type"}
+    for k, v in (default_args or {}).items():
+        kwargs.setdefault(k, v)
+    return cls(**kwargs)
 
 
 def registries():
@@ -79,22 +77,42 @@ def registries():
     return sys.modules[__name__], False
 
 
-def runner_to_cuda(self, batch):
-    for k in batch:
-        if k == 'meta':
-            continue
-        if k == 'image_name':
-            continue
-        if isinstance(batch[k], list):
-            if isinstance(batch[k][0], torch.Tensor):
-                batch[k] = [ item.unsqueeze(0) for item in batch[k]]
-                batch[k] = torch.cat(batch[k], dim=0).cuda()
-            elif isinstance(batch[k][0], np.ndarray):
-                batch[k] = [ torch.from_numpy(item).unsqueeze(0) for item in batch[k]]
-                batch[k] = torch.cat(batch[k], dim=0).cuda()
-            else:
-                batch[k] = [item.cuda() for item in batch[k]]
-        else:
-            batch[k] = batch[k].cuda(non_blocking=True)
+def _to_device(t):
+    return t.cuda()
 
+
+def runner_to_cuda(self, batch):
+    """What reference baseline/engine/runner.py:125-152 (``Runner.to_cuda``) does to a collated batch, in our own words:
+    'meta' and 'image_name' stay; a LIST of tensors (or ndarrays) is stacked along a new first axis -- which needs
+    equal shapes, hence ``PointBatch`` -- and moved; a list of anything else is moved item by item; every other
+    entry is moved with ``.cuda(non_blocking=True)``.  tests/test_plugins.py runs it side by side with the method
+    extracted from the reference file."""
+    for key in batch:
+        if key in ("meta", "image_name"):
+            continue
+        value = batch[key]
+        if not isinstance(value, list):
+            batch[key] = value.cuda(non_blocking=True)
+        elif isinstance(value[0], torch.Tensor):
+            batch[key] = _to_device(torch.cat([v.unsqueeze(0) for v in value], dim=0))
+        elif isinstance(value[0], np.ndarray):
+            batch[key] = _to_device(torch.cat([torch.from_numpy(v).unsqueeze(0) for v in value], dim=0))
+        else:
+            batch[key] = [v.cuda() for v in value]
     return batch
+
+
+def load_reference_to_cuda():
+    """``Runner.to_cuda`` cut out of the reference's runner.py (the module itself needs mmcv & co.); None if absent."""
+    import ast
+    import textwrap
+    path = os.path.join(REF_ROOT, "baseline", "engine", "runner.py")
+    if not os.path.exists(path):
+        return None
+    src = open(path).read()
+    tree = ast.parse(src)
+    fn = next(n for c in ast.walk(tree) if isinstance(c, ast.ClassDef) and c.name == "Runner"
+              for n in c.body if isinstance(n, ast.FunctionDef) and n.name == "to_cuda")
+    ns = {"torch": torch, "np": np}
+    exec(textwrap.dedent(ast.get_source_segment(src, fn)), ns)
+    return ns["to_cuda"]

@@ -6,13 +6,11 @@ way ``baseline/models/registry.py:5-36`` and ``baseline/datasets/registry.py:15-
 registered and built with ``build_from_cfg``, and the on-the-fly dataset runs inside a forked
 ``DataLoader(num_workers=2, pin_memory=...)`` with ``collate_points`` exactly as
 ``baseline/datasets/registry.py:54-59`` builds its loader.
-GPU part: the batch goes through ``Runner.to_cuda`` (restated, AST-equal to the reference) and a
+GPU part: the batch goes through ``Runner.to_cuda`` (a stand-in held equal to the reference's method on the same batches) and a
 ``Detector1stage``-shaped net under ``nn.DataParallel`` (reference baseline/engine/runner.py:103).
 """
-import ast
 import json
 import os
-import textwrap
 
 import numpy as np
 import pytest
@@ -94,16 +92,56 @@ def test_restated_registry_behaves_like_the_reference():
             R.register_module(lambda: 0)
 
 
-def test_restated_to_cuda_is_the_reference_method():
-    path = os.path.join(RC.REF_ROOT, "baseline", "engine", "runner.py")
-    if not os.path.exists(path):
+class _Movable:
+    """An object with .cuda(): what a list of non-tensors holds in the reference's batches (mmdet3d point containers)."""
+
+    def __init__(self, v):
+        self.v, self.moved = v, False
+
+    def cuda(self, *a, **k):
+        m = _Movable(self.v)
+        m.moved = True
+        return m
+
+
+def test_restated_to_cuda_behaves_like_the_reference_method(monkeypatch):
+    """``Runner.to_cuda`` cut out of the reference's runner.py and our stand-in, side by side on the same batches
+    (``.cuda`` patched to the identity: there is no GPU here).  Both crash on a ragged list of clouds -- the reason
+    ``collate_points`` returns a ``PointBatch`` -- and both move a ``PointBatch`` through its own ``.cuda``."""
+    ref_to_cuda = RC.load_reference_to_cuda()
+    if ref_to_cuda is None:
         pytest.skip("/root/reference is not mounted")
-    tree = ast.parse(open(path).read())
-    ref_fn = next(n for c in ast.walk(tree) if isinstance(c, ast.ClassDef) and c.name == "Runner"
-                  for n in c.body if isinstance(n, ast.FunctionDef) and n.name == "to_cuda")
-    import inspect
-    mine = ast.parse(textwrap.dedent(inspect.getsource(RC.runner_to_cuda))).body[0]
-    assert ast.dump(ast.Module(ref_fn.body, [])) == ast.dump(ast.Module(mine.body, []))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(lm_datasets.PointBatch, "cuda", lambda self, *a, **k: ("moved", self))
+
+    def batches():
+        g = torch.Generator().manual_seed(0)
+        return [
+            {"proj": torch.rand(2, 3, 4, 4, generator=g), "image_name": ["a", "b"], "meta": {"k": 1}},
+            {"label": [torch.ones(3, 2), torch.zeros(3, 2)], "arr": [np.ones((2, 2), np.float32), np.zeros((2, 2), np.float32)]},
+            {"objs": [_Movable(1), _Movable(2)], "x": torch.arange(4)},
+            {"points": lm_datasets.PointBatch.from_list([torch.rand(5, 4, generator=g), torch.rand(3, 4, generator=g)]),
+             "bev_geom": torch.zeros(2, 8)},
+        ]
+
+    def norm(v):
+        if isinstance(v, torch.Tensor):
+            return ("tensor", tuple(v.shape), v.tolist())
+        if isinstance(v, list):
+            return [norm(x) for x in v]
+        if isinstance(v, _Movable):
+            return ("movable", v.v, v.moved)
+        if isinstance(v, tuple) and v and v[0] == "moved":
+            return ("pointbatch moved", len(v[1]))
+        return v
+
+    for b_ref, b_own in zip(batches(), batches()):
+        got_ref, got_own = ref_to_cuda(None, b_ref), RC.runner_to_cuda(None, b_own)
+        assert {k: norm(v) for k, v in got_ref.items()} == {k: norm(v) for k, v in got_own.items()}
+    ragged = lambda: {"points": [torch.zeros(5, 4), torch.zeros(3, 4)]}
+    for fn in (ref_to_cuda, RC.runner_to_cuda):
+        with pytest.raises(RuntimeError):
+            fn(None, ragged())
 
 
 def build_plugins():
