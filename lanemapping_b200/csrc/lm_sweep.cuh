@@ -7,7 +7,7 @@
 // record ring stays resident in the 126 MB L2 while the 16 B/pt point stream flows through it (ring
 // <= 20 MB, point loads marked evict-first: DRAM write-back of the ring ~0, re-reads all hit).  So:
 //
-//   PRODUCER CTAs (3 per SM) claim 1024-point batches in stream order, stage them with TMA bulk copies,
+//   PRODUCER CTAs (2 per SM) claim 1024-point batches in stream order, stage them with TMA bulk copies (3 stages),
 //     compute the cell keys exactly as bin_points does, and route every point as ONE 32-bit record to the
 //     CTA that OWNS its cell: per-owner rings in shared memory, flushed as 32-byte granules (8 records)
 //     into a per-(producer, owner) mailbox ring in global memory that never leaves L2.
@@ -15,6 +15,8 @@
 //     rows so that every owner sees the whole cross-track density profile) and keep a sliding window of
 //     SW_R rows of their cells' accumulators in shared memory.  They poll their mailboxes, reduce the
 //     records with shared-memory atomics, and emit finished rows (u8 HWC image / u16 count / f32 proj).
+//   Measured (B200, config 2): exact, DRAM traffic 0.99 x the algorithmic bytes, 2.1 ms -- slower than the two-pass path
+//   (0.525 ms): the consumers' 8 warps per SM are latency-bound.  Opt-in, experimental.
 //
 // Exact by construction, for ANY input order:
 //   * a granule's words carry a phase bit (ring-wrap parity): a consumer takes a granule only when all 8
