@@ -850,17 +850,19 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(Ws ws, KParams kp) {
 __global__ void index_chunks_kernel(Ws ws) {
     if (gated_off(ws)) return;
     if (ws.stats->error & LM_DEV_ERR_POOL) return;
-    // chunk ids are (bin CTA, local id) pairs: CTA b used local ids 1 .. cta_chunks[b] of its region
-    const uint32_t total = ws.bin_grid * ws.region;
-    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < total; id += gridDim.x * blockDim.x) {
-        const uint32_t b = id / ws.region, k = id - b * ws.region;
-        if (k == 0 || k > ws.cta_chunks[b]) continue;
-        const uint2 m = ws.chunk_meta[id];           // every allocated chunk was published with count >= 1
-        const uint32_t np = (m.y + PIECE_RECS - 1) / PIECE_RECS;               // non-empty pieces of this chunk
-        const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], np);
-        for (uint32_t q = 0; q < np; ++q) {
-            const uint32_t c = min(m.y - q * PIECE_RECS, (uint32_t)PIECE_RECS);
-            ws.chunk_index[slot + q] = (id * HALVES + q) | ((c - 1u) << IDX_ID_BITS);
+    // chunk ids are (bin CTA, local id) pairs: CTA b used local ids 1 .. cta_chunks[b] of its region.  One block walks
+    // one bin CTA's used ids (not the whole id space: a region is mostly unused reservation)
+    for (uint32_t b = blockIdx.x; b < ws.bin_grid; b += gridDim.x) {
+        const uint32_t used = ws.cta_chunks[b];
+        for (uint32_t k = 1u + threadIdx.x; k <= used; k += blockDim.x) {
+            const uint32_t id = b * ws.region + k;
+            const uint2 m = ws.chunk_meta[id];           // every allocated chunk was published with count >= 1
+            const uint32_t np = (m.y + PIECE_RECS - 1) / PIECE_RECS;               // non-empty pieces of this chunk
+            const uint32_t slot = ws.tile_first[m.x] + atomicAdd(&ws.tile_cursor[m.x], np);
+            for (uint32_t q = 0; q < np; ++q) {
+                const uint32_t c = min(m.y - q * PIECE_RECS, (uint32_t)PIECE_RECS);
+                ws.chunk_index[slot + q] = (id * HALVES + q) | ((c - 1u) << IDX_ID_BITS);
+            }
         }
     }
 }
