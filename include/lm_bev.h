@@ -122,7 +122,10 @@ typedef struct lm_bev_stats {
     uint32_t n_chunks;      /* record chunks used by the binned path                    */
     uint64_t n_valid;       /* points that fell inside the window                       */
     uint32_t n_tiles;       /* shared-memory tiles of the binned path                   */
-    uint32_t reserved[3];
+    uint32_t ct_overflow;   /* 1: the compact-table pass met more tiles per CTA than its  */
+                            /* table holds and the direct-indexed kernels redid the call  */
+                            /* (informational: the result is exact either way)            */
+    uint32_t reserved[2];
 } lm_bev_stats;
 
 int         lm_bev_abi_version(void);
@@ -177,7 +180,9 @@ typedef struct lm_bev_tuning {
     int32_t max_tiles;         /* tiles per launch; smaller values force the in-call row-window loop (tests)     */
     int32_t stream_hint;       /* 1: the point stream is loaded with an L2 evict-first policy                    */
     int32_t use_graph;         /* 1: lm_bev_plan_rasterize replays a captured graph while the arguments repeat   */
-    int32_t reserved[2];
+    int32_t bin_compact_table; /* bin_points keeps its per-tile append state in a per-CTA hash table (4 CTAs per SM for any tile */
+                               /* count): 0 = when direct indexing would run < 3 CTAs per SM, 1 = always, -1 = never         */
+    int32_t reserved;
 } lm_bev_tuning;
 typedef struct lm_bev_plan lm_bev_plan;
 

@@ -41,7 +41,8 @@ class LmBevOutputs(C.Structure):
 
 class LmBevTuning(C.Structure):
     _fields_ = [("bin_ctas_per_sm", C.c_int32), ("red_ctas_per_sm", C.c_int32), ("tile_h_log2", C.c_int32),
-                ("max_tiles", C.c_int32), ("stream_hint", C.c_int32), ("use_graph", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("max_tiles", C.c_int32), ("stream_hint", C.c_int32), ("use_graph", C.c_int32), ("bin_compact_table", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class LmBevSampleGeom(C.Structure):
@@ -83,7 +84,7 @@ class LmBevStats(C.Structure):
     _fields_ = [
         ("error", C.c_uint32), ("n_chunks", C.c_uint32),
         ("n_valid", C.c_uint64),
-        ("n_tiles", C.c_uint32), ("reserved", C.c_uint32 * 3),
+        ("n_tiles", C.c_uint32), ("ct_overflow", C.c_uint32), ("reserved", C.c_uint32 * 2),
     ]
 
 

@@ -203,7 +203,7 @@ class BevRasterizer:
         raw = self.workspace[:C.sizeof(_cabi.LmBevStats)].cpu().numpy().tobytes()
         s = _cabi.LmBevStats.from_buffer_copy(raw)
         return {"error": int(s.error), "n_chunks": int(s.n_chunks), "n_valid": int(s.n_valid),
-                "n_tiles": int(s.n_tiles)}
+                "n_tiles": int(s.n_tiles), "ct_overflow": int(s.ct_overflow)}
 
     def check_device_errors(self) -> None:
         s = self.stats()
@@ -302,7 +302,7 @@ class BatchRasterizer:
         raw = self.workspace[:C.sizeof(_cabi.LmBevStats)].cpu().numpy().tobytes()
         s = _cabi.LmBevStats.from_buffer_copy(raw)
         return {"error": int(s.error), "n_chunks": int(s.n_chunks), "n_valid": int(s.n_valid),
-                "n_tiles": int(s.n_tiles)}
+                "n_tiles": int(s.n_tiles), "ct_overflow": int(s.ct_overflow)}
 
 
 def las_xform(header, params=None):

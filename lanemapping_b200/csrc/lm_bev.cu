@@ -161,7 +161,7 @@ struct Outs {
 thread_local char g_err[512] = "";
 // Tuning knobs of the call in progress (a plan's, include/lm_bev.h lm_bev_tuning; all-zero = defaults for the
 // plain entry points).  Nothing in the library reads the process environment.
-const lm_bev_tuning k_default_tuning = {0, 0, 0, 0, 0, 0, {0, 0}};
+const lm_bev_tuning k_default_tuning = {};
 thread_local const lm_bev_tuning *g_tune = &k_default_tuning;
 struct TuneScope {
     const lm_bev_tuning *prev;
@@ -522,7 +522,32 @@ __device__ __forceinline__ void scan_tiles_body(const Ws &ws, const KParams &kp,
 // LAS: the input is the point-data block of an uncompressed LAS file (record_length bytes per point)
 // and the decode of lm_dev.cuh::las_decode_record runs on the staged bytes; no float4 copy of the
 // cloud ever exists in HBM.
-template <bool BATCHED, bool LAS>
+// CT (compact table): the per-tile append state is not indexed by the tile id (8 B x T of shared memory: one CTA
+// per SM at config 4's 12 150 tiles) but lives in an open-addressing hash table of CT_SLOTS entries keyed by the tile id --
+// a CTA's contiguous range of a scan-ordered cloud touches a few hundred tiles however many the raster has.  4 CTAs per SM
+// for any T.  A CTA that meets more tiles than the table holds raises stats->ct_overflow and drops the record: the caller
+// has the direct-indexed kernels queued behind, gated on that word, and they redo the raster.
+constexpr int CT_SLOTS = 1024;
+constexpr uint32_t CT_EMPTY = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t atoms_cas_u32(uint32_t a, uint32_t cmp, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(v) : "memory");
+    return old;
+}
+// slot of `tile` in the table at sm_key (claims an empty slot on first sight); CT_EMPTY if the table is full
+__device__ __forceinline__ uint32_t ct_find(uint32_t sm_key, uint32_t tile) {
+    uint32_t s = (tile * 2654435761u) >> (32 - 10);
+    static_assert(CT_SLOTS == 1 << 10, "hash width");
+    for (int probe = 0; probe < CT_SLOTS; ++probe) {
+        uint32_t k = lds_u32(sm_key + 4u * s);
+        if (k == CT_EMPTY) k = atoms_cas_u32(sm_key + 4u * s, CT_EMPTY, tile);
+        if (k == tile || k == CT_EMPTY) return s;            // found, or claimed just now
+        s = (s + 1u) & (CT_SLOTS - 1);
+    }
+    return CT_EMPTY;
+}
+
+template <bool BATCHED, bool LAS, bool CT = false>
 __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 *__restrict__ pts, long long n, const Ws &ws,
                                                 const BatchTab *btp, const LasXform *xfp) {
     const BatchTab &bt = *btp;       // only dereferenced when BATCHED
@@ -531,11 +556,12 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
     // one stage buffer: a full batch of records, 16-byte granular, + one spare 16 B (whole words are read)
     const uint32_t stage_bytes = LAS ? ((BIN_BATCH * rec_bytes + 15u) & ~15u) + 16u : BIN_BATCH * 16u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = kp.T;
-    // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u16
+    const int T = CT ? CT_SLOTS : kp.T;          // entries of the append-state arrays (CT: table slots)
+    // layout: stage[2][BIN_BATCH] float4 (TMA double buffer) | pos[T] u32 | slot[T][NSLOT] u16 | CT: key[CT_SLOTS] u32
     uint32_t sm_stage = smem_u32(smem_raw);
     uint32_t sm_pos = sm_stage + (uint32_t)BIN_STAGES * stage_bytes;
     uint32_t sm_slot = sm_pos + (uint32_t)T * 4u;
+    const uint32_t sm_key = sm_slot + (uint32_t)T * 2u * NSLOT;
     // keep the three bases in registers: without this the compiler re-derives them (window base +
     // offsets, ~5 instructions) at every use because they are cheap to rematerialise
     asm volatile("" : "+r"(sm_stage), "+r"(sm_pos), "+r"(sm_slot));
@@ -555,6 +581,7 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
     const uint32_t sm_next = smem_u32(&s_next);
     const uint32_t region_base = blockIdx.x * ws.region;
     for (int t = tid; t < T; t += BIN_THREADS) sts_u32(sm_pos + 4u * t, 0u);
+    if (CT) for (int t = tid; t < CT_SLOTS; t += BIN_THREADS) sts_u32(sm_key + 4u * t, CT_EMPTY);
     __syncthreads();
 
     const long long nb = BATCHED ? (long long)bt.first[bt.nb] : (n + BIN_BATCH - 1) / BIN_BATCH;
@@ -700,11 +727,23 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         }
         // ---- phase 1: reserve.  The first record of a chunk block allocates the block's chunk.
         uint32_t sa[BIN_PPT];                                    // shared address of the point's ring slot
+        uint32_t en[BIN_PPT];                                    // entry of the append state: the tile id, or its table slot
+#pragma unroll
+        for (int j = 0; j < BIN_PPT; ++j) {
+            en[j] = tl[j];
+            if (CT && tl[j] != INVALID_U32) {
+                en[j] = ct_find(sm_key, tl[j]);
+                if (en[j] == CT_EMPTY) {                         // more tiles than the table holds: the gated kernels redo the call
+                    atomicExch(&ws.stats->ct_overflow, 1u);
+                    tl[j] = INVALID_U32;
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < BIN_PPT; ++j) {
             if (tl[j] != INVALID_U32) {
-                ps[j] = atoms_add(sm_pos + 4u * tl[j], 1u);
-                sa[j] = sm_slot + (2u * NSLOT) * tl[j] + ((ps[j] >> (CHUNK_LOG2 - 1)) & (2u * (NSLOT - 1)));   // ring slot of its block
+                ps[j] = atoms_add(sm_pos + 4u * en[j], 1u);
+                sa[j] = sm_slot + (2u * NSLOT) * en[j] + ((ps[j] >> (CHUNK_LOG2 - 1)) & (2u * (NSLOT - 1)));   // ring slot of its block
                 if ((ps[j] & (CHUNK_RECS - 1)) == 0) {
                     uint32_t id = atoms_add(sm_next, 1u);
                     if (id >= ws.region) {                       // cannot happen with lm_bev_workspace_bytes' size
@@ -728,7 +767,7 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
                 const uint32_t off = ps[j] & (CHUNK_RECS - 1);
                 ws.pool[cid[j] * (uint32_t)CHUNK_RECS + off] = rec[j];        // record index < 2^32 (checked on the host)
                 if (off == 0 && ps[j] != 0) {                    // the previous block of this tile is complete
-                    const uint32_t prev = lds_u16(sm_slot + 2u * (tl[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
+                    const uint32_t prev = lds_u16(sm_slot + 2u * (en[j] * NSLOT + (((ps[j] >> CHUNK_LOG2) - 1u) & (NSLOT - 1))));
                     if (prev) publish_chunk(ws, region_base + prev, CHUNK_RECS, tl[j]);
                 }
             }
@@ -743,7 +782,7 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
             my_valid += q;
             const uint32_t last = q - 1;
             const uint32_t id = lds_u16(sm_slot + 2u * (t * NSLOT + ((last >> CHUNK_LOG2) & (NSLOT - 1))));
-            if (id) publish_chunk(ws, region_base + id, (last & (CHUNK_RECS - 1)) + 1u, (uint32_t)t);
+            if (id) publish_chunk(ws, region_base + id, (last & (CHUNK_RECS - 1)) + 1u, CT ? lds_u32(sm_key + 4u * t) : (uint32_t)t);
         }
     }
     for (int o = 16; o; o >>= 1) my_valid += __shfl_xor_sync(0xffffffffu, my_valid, o);
@@ -773,6 +812,13 @@ __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_kerne
                                                                                long long n, Ws ws) {
     if (gated_off(ws)) return;
     bin_points_body<false, false>(kp, pts, n, ws, nullptr, nullptr);
+}
+__global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_ct_kernel(KParams kp, const float4 *__restrict__ pts,
+                                                                                  long long n, Ws ws) {
+    bin_points_body<false, false, true>(kp, pts, n, ws, nullptr, nullptr);
+}
+__global__ void ct_epilogue_kernel(lm_bev_stats *stats) {      // behind a compact-table pass that overflowed: the gated kernels count again
+    if (stats->ct_overflow) { stats->n_valid = 0; stats->n_chunks = 0; }
 }
 __global__ void __launch_bounds__(BIN_THREADS, LM_BIN_MIN_CTAS) bin_points_batch_kernel(KParams kp, const __grid_constant__ BatchTab bt,
                                                                                      Ws ws) {
@@ -893,6 +939,8 @@ __device__ __forceinline__ void store_pixels4(uint8_t *dst, const uint32_t pk[4]
         w[0] = (pk[0] & 0xFFFFFFu) | (pk[1] << 24);
         w[1] = ((pk[1] >> 8) & 0xFFFFu) | (pk[2] << 16);
         w[2] = ((pk[2] >> 16) & 0xFFu) | (pk[3] << 8);
+    } else if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     } else {
         w[0] = pk[0]; w[1] = pk[1]; w[2] = pk[2]; w[3] = pk[3];
     }
@@ -1027,6 +1075,16 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     __shared__ uint32_t s_in, s_cnt;                     // records streamed into / counted in the current tile
     __shared__ float s_div255[256];                      // u8 / 255 (one IEEE division each): the proj values
     if (out.proj) for (int i = tid; i < 256; i += RED_THREADS) s_div255[i] = __fdiv_rn((float)i, 255.0f);
+    // Every candidate channel value is one byte.  They sit in two registers, A = [max_z | min_z | mean_i | max_i] and
+    // B = [0 | 0 | density | mean_z], and ONE byte permute with this selector assembles a pixel's output word
+    // (nibble c = which of the eight bytes channel c takes; byte 6 is zero for the channels past nch).
+    uint32_t ch_sel = 0;
+    for (int c = 0; c < 4; ++c) {
+        const int ch = c < kp.nch ? kp.ch[c] : -1;
+        const uint32_t idx = ch == LM_CH_MAX_I ? 0u : ch == LM_CH_MEAN_I ? 1u : ch == LM_CH_MIN_Z ? 2u : ch == LM_CH_MAX_Z ? 3u
+                           : ch == LM_CH_MEAN_Z ? 4u : ch == LM_CH_DENSITY ? 5u : 6u;
+        ch_sel |= idx << (4 * c);
+    }
     auto zero_tile = [&]() {
         uint4 *a4 = reinterpret_cast<uint4 *>(acc);
         const int n4 = NW * cells / 4;
@@ -1053,6 +1111,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         // ---- stream the tile's chunks with integer atomics in shared memory; count+sum packed in one
         //      word when possible, redone unpacked if a cell's count field overflowed
         constexpr bool CAN_PACK = (MASK & M_CNT) && (MASK & (M_SUMZ | M_SUMI));
+        constexpr bool PACK_Z = CAN_PACK && (MASK & M_SUMZ), PACK_I = CAN_PACK && !PACK_Z;     // as in accumulate_rec
         for (int round = 0; round < 2; ++round) {                // round 1 only after a wrapped packed count
         const bool packed_ok = CAN_PACK && round == 0;
         if (packed_ok) {
@@ -1068,7 +1127,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         //      covers a whole 128-cell tile row), derives the channels, assembles the output words in
         //      registers and stores them directly; the planes are zeroed for the next tile on the way
         const size_t gcells = (size_t)kp.oH * kp.W;
-        const int nch = kp.nch, ch0 = kp.ch[0], ch1 = kp.ch[1], ch2 = kp.ch[2], ch3 = kp.ch[3];
+        const int nch = kp.nch;
         const size_t row_bytes = (size_t)kp.W * nch;
         const bool full_w = ncols == TILE_W;
         const bool img_fast = full_w && (row_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(out.image) & 3) == 0;
@@ -1084,8 +1143,9 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             const uint4 z4 = make_uint4(0, 0, 0, 0);
             uint4 vc = z4, vsi = z4, vsz = z4, vmi = z4, vnz = z4, vxz = z4;
             if (MASK & M_CNT) { vc = *reinterpret_cast<uint4 *>(a_cnt + cell0); *reinterpret_cast<uint4 *>(a_cnt + cell0) = z4; }
-            if (MASK & M_SUMI) { vsi = *reinterpret_cast<uint4 *>(a_sumi + cell0); *reinterpret_cast<uint4 *>(a_sumi + cell0) = z4; }
-            if (MASK & M_SUMZ) { vsz = *reinterpret_cast<uint4 *>(a_sumz + cell0); *reinterpret_cast<uint4 *>(a_sumz + cell0) = z4; }
+            // (the sum that shares the count's word in a packed round has an idle plane: still zero, not read)
+            if ((MASK & M_SUMI) && !(packed_ok && PACK_I)) { vsi = *reinterpret_cast<uint4 *>(a_sumi + cell0); *reinterpret_cast<uint4 *>(a_sumi + cell0) = z4; }
+            if ((MASK & M_SUMZ) && !(packed_ok && PACK_Z)) { vsz = *reinterpret_cast<uint4 *>(a_sumz + cell0); *reinterpret_cast<uint4 *>(a_sumz + cell0) = z4; }
             if (MASK & M_MAXI) { vmi = *reinterpret_cast<uint4 *>(a_maxi + cell0); *reinterpret_cast<uint4 *>(a_maxi + cell0) = z4; }
             if (MASK & M_MINZ) { vnz = *reinterpret_cast<uint4 *>(a_minz + cell0); *reinterpret_cast<uint4 *>(a_minz + cell0) = z4; }
             if (MASK & M_MAXZ) { vxz = *reinterpret_cast<uint4 *>(a_maxz + cell0); *reinterpret_cast<uint4 *>(a_maxz + cell0) = z4; }
@@ -1126,15 +1186,7 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
                     }
                 }
                 const uint32_t dens = cnt < 255u ? cnt : 255u;
-                auto pick = [&](int ch) -> uint32_t {
-                    return ch == LM_CH_MAX_I ? mi : ch == LM_CH_MEAN_I ? mean_i : ch == LM_CH_MIN_Z ? nz
-                         : ch == LM_CH_MAX_Z ? xz : ch == LM_CH_MEAN_Z ? mean_z : dens;
-                };
-                uint32_t v = pick(ch0);
-                if (nch > 1) v |= pick(ch1) << 8;
-                if (nch > 2) v |= pick(ch2) << 16;
-                if (nch > 3) v |= pick(ch3) << 24;
-                pk[e] = v;
+                pk[e] = __byte_perm(mi | (mean_i << 8) | (nz << 16) | (xz << 24), mean_z | (dens << 8), ch_sel);
                 k16[e] = cnt < 65535u ? cnt : 65535u;
             }
             if (out.image) {
@@ -1154,7 +1206,9 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
             }
             if (out.count16) {
                 uint16_t *dst = out.count16 + grow;
-                if (c16_fast) {
+                if (c16_fast && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(k16[0] | (k16[1] << 16), k16[2] | (k16[3] << 16));
+                } else if (c16_fast) {
                     reinterpret_cast<uint32_t *>(dst)[0] = k16[0] | (k16[1] << 16);
                     reinterpret_cast<uint32_t *>(dst)[1] = k16[2] | (k16[3] << 16);
                 } else {
@@ -1375,6 +1429,9 @@ int cached_occupancy(const void *kernel, int threads, size_t smem, int *occ_out)
 }
 
 size_t bin_smem_bytes(int T) { return BIN_STAGES * (size_t)BIN_BATCH * sizeof(float4) + (size_t)T * (4 + 2 * NSLOT); }
+// compact-table bin_points: CT_SLOTS entries of append state + their keys, whatever the raster's tile count
+size_t bin_ct_smem_bytes() { return bin_smem_bytes(CT_SLOTS) + (size_t)CT_SLOTS * 4; }
+constexpr int CT_MAX_TILES = 1 << 18;     // tiles of a compact-table call (only the tile tables in global memory grow with it)
 
 // chunks per bin CTA when `grid` CTAs share `nb` batches: the chunks its points can fill, one open
 // chunk per tile, and the unused local id 0
@@ -1386,13 +1443,14 @@ long long bin_region(long long nb, long long grid, int T) {
 
 // upper bound of the bin_points grid for T tiles (shared memory limits the CTAs per SM); the record
 // pool reserves one open chunk per (CTA, tile), so the workspace size and the launch both use it
-int bin_ctas_bound(int T) {
+int bin_ctas_bound_smem(size_t smem) {
     const size_t per_sm = 227 * 1024;
-    size_t occ = per_sm / (bin_smem_bytes(T) + 1024);
+    size_t occ = per_sm / (smem + 1024);
     if (occ < 1) occ = 1;
     if (occ > (size_t)LM_BIN_MIN_CTAS + 1) occ = LM_BIN_MIN_CTAS + 1;
     return 148 * (int)occ;
 }
+int bin_ctas_bound(int T) { return bin_ctas_bound_smem(bin_smem_bytes(T)); }
 
 int max_tiles() {
     if (const int v = g_tune->max_tiles) {                  // test knob: forces the row-window loop on small rasters
@@ -1432,7 +1490,8 @@ int bin_ctas_for(long long n) {
 
 // Binned workspace: [stats | ctl | tile tables | chunks used per bin CTA] (zeroed per call)
 //                   [chunk side table | chunk index | record pool]
-int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L) {
+// ct: layout of the compact-table pass -- T only sizes the tile tables; a bin CTA holds at most CT_SLOTS open chunks
+int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L, bool ct = false) {
     memset(L, 0, sizeof(*L));
     size_t o = 0;
     o = align_up(o + sizeof(lm_bev_stats), 64);
@@ -1449,13 +1508,14 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L)
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
     L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
-    const long long gb = bin_ctas_bound(T);
+    const long long gb = ct ? bin_ctas_bound_smem(bin_ct_smem_bytes()) : bin_ctas_bound(T);
+    const int T_open = ct && T > CT_SLOTS ? CT_SLOTS : T;      // open chunks a bin CTA can hold
     L->off_cta = o;     o = align_up(o + (size_t)gb * 4, 256);
     L->zero_bytes = o;
     // every bin CTA owns a region of the pool (bin_region): whatever grid <= gb the launch ends up with,
     // grid * region <= batches + gb * (T + 2).  A batched call adds one partial batch per sample.
     const unsigned long long nbb = (unsigned long long)(n / BIN_BATCH) + 1ull + MAX_BATCH;
-    const unsigned long long chunks = nbb * CHUNKS_PER_BATCH + (unsigned long long)gb * ((unsigned long long)T + 2ull) + 1ull;
+    const unsigned long long chunks = nbb * CHUNKS_PER_BATCH + (unsigned long long)gb * ((unsigned long long)T_open + 2ull) + 1ull;
     if (chunks * HALVES >= (1ull << IDX_ID_BITS))     // piece ids share a word with the count; record indices are 32-bit
         return fail(LM_ERR_UNSUPPORTED, "record pool exceeds 2^23 chunks: shard the call (fewer points or a smaller row window)");
     L->pool_chunks = (uint32_t)chunks;
@@ -1516,7 +1576,10 @@ cudaError_t launch_sweep_mask(int mask, const KParams &kp, const float4 *pts, lo
 
 // Grid and chunk region of one bin launch (the same values in every stage-split call of a raster):
 // persistent, one wave of resident CTAs, each owning a contiguous range of the nb batches.
-int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles_x, int sms, const Layout &L, Ws *ws, int *grid_out) {
+int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles_x, int sms, const Layout &L, Ws *ws, int *grid_out,
+                 bool ct = false) {
+    const int bound = ct ? bin_ctas_bound_smem(bin_ct_smem_bytes()) : bin_ctas_bound(T);
+    if (ct && T > CT_SLOTS) T = CT_SLOTS;
     if (smem > 220 * 1024) return fail(LM_ERR_UNSUPPORTED, "%zu bytes of shared memory per bin CTA: too many tiles / too long records", smem);
     int occ = 1;
     if (int rc = cached_occupancy(kernel, BIN_THREADS, smem, &occ)) return rc;
@@ -1529,11 +1592,17 @@ int bin_geometry(const void *kernel, size_t smem, long long nb, int T, int tiles
     if (const int v = g_tune->bin_ctas_per_sm) {                  // tuning knob, 1 .. what the hardware holds
         if (v >= 1) occ = v < hw_occ ? v : hw_occ;
     }
-    long long grid = (long long)sms * (occ < 1 ? 1 : occ);
-    if (grid > bin_ctas_bound(T)) grid = bin_ctas_bound(T);
-    if (grid > nb) grid = nb;
-    if (grid < 1) grid = 1;
-    const long long region = bin_region(nb, grid, T);
+    long long grid = 0, region = 0;
+    // The pool was sized for the layout's own tile count; a launch with FEWER tiles (the shorter last row window of a
+    // raster) may fit more CTAs per SM and so reserve more open chunks than that: run it with fewer CTAs then.
+    for (occ = occ < 1 ? 1 : occ;; --occ) {
+        grid = (long long)sms * occ;
+        if (grid > bound) grid = bound;
+        if (grid > nb) grid = nb;
+        if (grid < 1) grid = 1;
+        region = bin_region(nb, grid, T);
+        if (occ == 1 || (region <= (long long)MAX_REGION && (unsigned long long)grid * (unsigned long long)region <= L.pool_chunks)) break;
+    }
     if (region > (long long)MAX_REGION)
         return fail(LM_ERR_UNSUPPORTED, "%lld chunks per bin CTA exceed the 16-bit local chunk ids: shard the call", region);
     if ((unsigned long long)grid * (unsigned long long)region > L.pool_chunks)
@@ -1569,6 +1638,45 @@ cudaError_t launch_reduce_mask(int mask, const KParams &kp, const Ws &ws, const 
     }
 }
 
+// ---- compact-table pass (bin_points_ct_kernel): when does a call take it, and with which tiles
+// tile height of the compact-table pass: its bin kernel does not care how many tiles there are, so rasters with four
+// planes or more take 32-row tiles (two or three reduce CTAs per SM instead of one)
+int ct_tile_h(int mask, const lm_bev_params *p) {
+    const int nw = popc6(mask);
+    if (const int v = g_tune->tile_h_log2) {
+        if (v >= 5 && v <= 7 && nw * (128 << v) * 4 <= 200 * 1024) return v;
+    }
+    return nw >= 4 ? 5 : tile_h_log2_for(mask, p->height, p->width);
+}
+// T_direct: tiles per launch of the direct-indexed kernels for this raster (one row window)
+bool ct_wanted(const lm_bev_params *p, int mask, int T_direct) {
+    const int mode = g_tune->bin_compact_table;           // 0 auto, 1 always, -1 never
+    if (mode < 0) return false;
+    if (make_kparams(p, ct_tile_h(mask, p)).T > CT_MAX_TILES) return false;
+    if (mode > 0) return true;
+    return bin_ctas_bound(T_direct) < 148 * 3;            // direct indexing would run fewer than three bin CTAs per SM
+}
+Ws bind_ws(unsigned char *w, const Layout &L) {
+    Ws ws;
+    ws.stats = reinterpret_cast<lm_bev_stats *>(w);
+    ws.ctl = reinterpret_cast<Ctl *>(w + L.off_ctl);
+    ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
+    ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
+    ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
+    ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
+    ws.cta_chunks = reinterpret_cast<uint32_t *>(w + L.off_cta);
+    ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
+    ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
+    ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
+    ws.acc = nullptr;
+    ws.pool_chunks = L.pool_chunks;
+    ws.gate = nullptr;
+    ws.region = 1;
+    ws.bin_grid = 0;
+    ws.scan_in_bin = false;
+    return ws;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1588,12 +1696,13 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
     // the tile height depends on the accumulator planes the outputs need.  Without an output set the bound has to
     // hold for every one: the pool reserves bin_ctas_bound(T) * (T + 2) chunks, which is NOT monotonic in the tile
     // count T (the CTAs per SM drop as T grows), so take the maximum over the three tile heights
-    int th_lo = 5, th_hi = 7;
+    int th_lo = 5, th_hi = 7, mask_of_out = 0;
     if (out) {
         const bool want16 = out->count16_dev != nullptr;
         const bool banded = out->acc_dev != nullptr && out->acc_band > 0 &&
                             (out->image_dev || out->count16_dev || out->proj_dev);
-        th_lo = th_hi = tile_h_log2_for(pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16), p->height, p->width);
+        mask_of_out = pick_mask(needed_mask(p, want16, out->acc_dev != nullptr && !banded), want16);
+        th_lo = th_hi = tile_h_log2_for(mask_of_out, p->height, p->width);
     }
     size_t best = 0;
     for (int th = th_lo; th <= th_hi; ++th) {
@@ -1609,6 +1718,17 @@ int lm_bev_workspace_bytes(const lm_bev_params *p, int64_t n_points, int algo, c
         rc = make_layout(p, n_points, algo, k.T, &L);
         if (rc) return rc;
         if (L.total > best) best = L.total;
+        // the compact-table pass of the same call (ct_wanted; k.T is the tile count of one direct-indexed launch):
+        // its own tile height, no row windows
+        const int mode = algo == LM_ALGO_BINNED ? g_tune->bin_compact_table : -1;
+        if (mode > 0 || (mode == 0 && bin_ctas_bound(k.T) < 148 * 3)) {
+            int tc_lo = 5, tc_hi = 7;
+            if (out) tc_lo = tc_hi = ct_tile_h(mask_of_out, p);
+            for (int tc = tc_lo; tc <= tc_hi; ++tc) {
+                const KParams kc = make_kparams(p, tc);
+                if (kc.T <= CT_MAX_TILES && make_layout(p, n_points, algo, kc.T, &L, true) == LM_OK && L.total > best) best = L.total;
+            }
+        }
     }
     *bytes = best;
     return LM_OK;
@@ -1717,20 +1837,38 @@ static int rasterize_impl(const lm_bev_params *p, const float *points_dev, int64
     rc = make_layout(p, n_points, algo, make_kparams(&pw, th).T, &L);
     if (rc) return rc;
     if (workspace_bytes < L.total) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, L.total);
-    Ws ws;
-    ws.stats = reinterpret_cast<lm_bev_stats *>(w);
-    ws.ctl = reinterpret_cast<Ctl *>(w + L.off_ctl);
-    ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
-    ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
-    ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
-    ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
-    ws.cta_chunks = reinterpret_cast<uint32_t *>(w + L.off_cta);
-    ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
-    ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
-    ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
-    ws.acc = nullptr;
-    ws.pool_chunks = L.pool_chunks;
-    ws.gate = nullptr;
+    Ws ws = bind_ws(w, L);
+
+    // ---- compact-table pass: the whole raster in one launch set, four bin CTAs per SM whatever the tile count.  The
+    //      direct-indexed kernels below stay queued behind it, gated on stats->ct_overflow (a bin CTA met more tiles
+    //      than its table holds: a cloud in no spatial order), and redo the raster in that case.
+    if (algo == LM_ALGO_BINNED && stages == LM_STAGE_ALL && !keep_stats && !las && n_points > 0 &&
+        ct_wanted(p, mask, make_kparams(&pw, th).T)) {
+        KParams kp = make_kparams(p, ct_tile_h(mask, p));
+        kp.band = banded ? out->acc_band : 0;
+        Layout Lc;
+        rc = make_layout(p, n_points, algo, kp.T, &Lc, true);
+        if (rc) return rc;
+        if (workspace_bytes < Lc.total) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, Lc.total);
+        Ws wc = bind_ws(w, Lc);
+        wc.scan_in_bin = n_points <= SCAN_IN_BIN_MAX_POINTS;
+        const long long nb = (n_points + BIN_BATCH - 1) / BIN_BATCH;
+        int grid = 0;
+        rc = bin_geometry((const void *)bin_points_ct_kernel, bin_ct_smem_bytes(), nb, kp.T, kp.tiles_x, sms, Lc, &wc, &grid, true);
+        if (rc) return rc;
+        cudaError_t e = cudaMemsetAsync(w, 0, Lc.zero_bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+        bin_points_ct_kernel<<<grid, BIN_THREADS, bin_ct_smem_bytes(), st>>>(kp, reinterpret_cast<const float4 *>(points_dev), n_points, wc);
+        if (!wc.scan_in_bin) scan_tiles_kernel<<<1, 1024, 0, st>>>(wc, kp);
+        index_chunks_kernel<<<sms * 4, 256, 0, st>>>(wc);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "compact-table bin/index launch");
+        e = launch_reduce_mask(mask, kp, wc, o, sms, st);
+        if (e != cudaSuccess) return cuda_fail(e, "compact-table reduce launch");
+        ct_epilogue_kernel<<<1, 1, 0, st>>>(wc.stats);
+        ws.gate = &ws.stats->ct_overflow;
+        keep_stats = true;                     // the gated kernels' memsets leave the stats block (and the gate in it) alone
+    }
     bool sweep = algo == LM_ALGO_SWEEP && sweep_eligible(p, out, mask, n_win, las != nullptr);
     SweepWs sw;
     if (sweep) {

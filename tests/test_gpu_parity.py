@@ -276,3 +276,80 @@ def test_plan_graph_replay_and_tuning_fields(bev):
         assert np.array_equal(rt(dev[1])["image"].cpu().numpy(), want[1]), tuning
     with pytest.raises(ValueError):
         bev.BevRasterizer(spec, 10, tuning={"no_such_knob": 1})
+
+
+def _ct_run(bev, cloud, spec, outputs, tuning):
+    r = bev.BevRasterizer(spec, max(1, len(cloud)), outputs=outputs, tuning=tuning)
+    out = r(torch.from_numpy(np.ascontiguousarray(cloud)).cuda())
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}, r.stats()
+
+
+@pytest.mark.parametrize("order", ["scan", "shuffled"])
+@pytest.mark.parametrize("channels,count16", [(CFG2_CH, False), (CFG4_CH, True)])
+def test_compact_table_bin_pass(bev, order, channels, count16):
+    """bin_points' compact-table variant (tuning bin_compact_table = 1; automatic on rasters whose tile count leaves
+    direct indexing fewer than three CTAs per SM): same bits as the oracle, a scan-ordered cloud never overflows the
+    table, and the stats count every point once."""
+    from oracle import c_oracle as CO
+    spec = BevSpec(2304, 1152, channels=channels, count16=count16, local_min_ele=default_min_ele(BevSpec(2304, 1152)))
+    cloud = make_cloud(1_500_000, spec, order=order, seed=5)
+    outputs = ["image", "proj"] + (["count16"] if count16 else [])
+    want = CO.rasterize(cloud, spec)
+    for tuning in ({"bin_compact_table": 1}, {"bin_compact_table": 1, "tile_h_log2": 6}):
+        got, st = _ct_run(bev, cloud, spec, outputs, tuning)
+        assert st["error"] == 0 and st["ct_overflow"] == 0, st      # 162..648 tiles: the table holds them all
+        assert st["n_valid"] == int(want["n_valid"])
+        assert np.array_equal(got["image"], want["image"])
+        if count16:
+            assert np.array_equal(got["count16"], want["count16"])
+    off, st_off = _ct_run(bev, cloud, spec, outputs, {"bin_compact_table": -1})
+    assert np.array_equal(off["image"], want["image"]) and st_off["n_valid"] == st["n_valid"]
+
+
+@pytest.mark.parametrize("max_tiles", [0, 700])
+def test_compact_table_overflow_falls_back_exactly(bev, max_tiles):
+    """A cloud in no spatial order on a raster of 4608 tiles: every bin CTA meets more tiles than its 1024-slot table
+    holds, raises stats.ct_overflow, and the direct-indexed kernels queued behind the pass (row windows included)
+    redo the raster -- same bits, every point counted once.  The same raster in scan order stays on the pass."""
+    spec = BevSpec(4608, 4096, channels=CFG4_CH, count16=True, local_min_ele=default_min_ele(BevSpec(4608, 4096)))
+    outputs = ["image", "count16"]
+    tuning = {"bin_compact_table": 1}
+    if max_tiles:
+        tuning["max_tiles"] = max_tiles
+    for order, overflow in (("shuffled", 1), ("scan", 0)):
+        cloud = make_cloud(3_000_000, spec, order=order, seed=11)
+        ref, st_ref = run_gpu(bev, cloud, spec, "direct", outputs)
+        got, st = _ct_run(bev, cloud, spec, outputs, tuning)
+        assert st["error"] == 0 and st["ct_overflow"] == overflow, (order, st)
+        assert st["n_valid"] == st_ref["n_valid"]
+        assert np.array_equal(got["image"], ref["image"]) and np.array_equal(got["count16"], ref["count16"])
+
+
+def test_compact_table_with_banded_accumulators(bev):
+    spec = BevSpec(1440, 2304, channels=CFG2_CH, local_min_ele=default_min_ele(BevSpec(1440, 2304)))
+    cloud = make_cloud(1_000_000, spec, order="scan", seed=3)
+    pts = torch.from_numpy(cloud).cuda()
+    outs = {}
+    for mode in (1, -1):
+        r = bev.BevRasterizer(spec, len(cloud), outputs=("image", "acc"), acc_band=64, tuning={"bin_compact_table": mode})
+        o = r(pts)
+        torch.cuda.synchronize()
+        assert r.stats()["ct_overflow"] == 0
+        outs[mode] = {k: v.cpu().numpy() for k, v in o.items()}
+    assert np.array_equal(outs[1]["image"], outs[-1]["image"])
+    band = np.r_[0:64, 1440 - 64:1440]
+    for plane in (O.ACC_COUNT, O.ACC_SUM_Z, O.ACC_MAX_I):      # the planes max_i / mean_z / density need
+        assert np.array_equal(outs[1]["acc"][plane][band], outs[-1]["acc"][plane][band])
+
+
+def test_shorter_last_row_window_fits_the_pool(bev):
+    """Row windows: the record pool is sized for the first window's tile count.  A shorter last window has fewer
+    tiles, fits more bin CTAs per SM and would reserve MORE open chunks than that (200 tile rows x 27 = 5400 tiles run
+    two CTAs per SM, the last 192 x 27 = 5184 three): the launch then takes fewer CTAs instead of failing."""
+    spec = BevSpec(12544, 3456, img_reso=(0.02, 0.02), channels=(CH_MAX_I,), local_min_ele=default_min_ele(BevSpec(12544, 3456)))
+    cloud = make_cloud(2_000_000, spec, order="scan", seed=21)
+    ref, st_ref = run_gpu(bev, cloud, spec, "direct", ["image"])
+    got, st = _ct_run(bev, cloud, spec, ["image"], {"max_tiles": 5400, "tile_h_log2": 5, "bin_compact_table": -1})
+    assert st["error"] == 0 and st["n_valid"] == st_ref["n_valid"]
+    assert np.array_equal(got["image"], ref["image"])

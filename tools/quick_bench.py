@@ -11,6 +11,8 @@ ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--orders", default="scan,shuffled")
 ap.add_argument("--algos", default="binned,direct")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--tune", default="", help="';'-separated tuning variants of the binned call, each 'field=value,field=value' (e.g. "
+                "'bin_compact_table=1,tile_h_log2=5;bin_compact_table=-1'); timed after the default")
 ap.add_argument("--las", action="store_true", help="time the LAS front end (decode, fused LAS->BEV) on the cfg's cloud")
 a = ap.parse_args()
 spec, n = config_spec(a.cfg)
@@ -99,4 +101,15 @@ for order in a.orders.split(","):
         print(f"  {algo:7s} best {ms:8.3f} ms  median {np.median(ts):8.3f}  {n/ms/1e3:9.1f} Mpts/s  "
               f"{balg/ms/1e6:7.1f} GB/s alg ({balg/ms/1e6/6538*100:5.1f}% of 6538)  ws={r.workspace.numel()/1e9:.2f} GB stats={st}", flush=True)
         del r, out
+    for variant in [v for v in a.tune.split(";") if v]:
+        tuning = {k: int(v) for k, v in (kv.split("=") for kv in variant.split(","))}
+        outs = ["image"] + (["count16"] if spec.count16 else [])
+        r = BevRasterizer(spec, n, outputs=outs, tuning=tuning)
+        out = r.alloc_outputs()
+        ms = timed(lambda: r(pts, out=out), a.reps)
+        ref = BevRasterizer(spec, n, algo="direct", outputs=outs)(pts)
+        same = all(bool(torch.equal(out[k], ref[k])) for k in outs)
+        print(f"  tuning {variant}: best {ms:8.3f} ms  {spec.algorithmic_bytes(n)/ms/1e6/6538*100:5.1f}% of 6538  "
+              f"ws={r.workspace.numel()/1e9:.2f} GB  == direct: {same}  stats={r.stats()}", flush=True)
+        del r, out, ref
     del pts
