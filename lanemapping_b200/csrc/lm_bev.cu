@@ -133,7 +133,7 @@ struct Ws {                  // device pointers into the caller's workspace
     uint32_t *tile_nchunks;  // [T]
     uint32_t *tile_first;    // [T]
     uint32_t *tile_cursor;   // [T]
-    uint32_t *tile_order;    // [T] tiles sorted heaviest first (reduce_tiles schedule)
+    uint4 *tile_sched;       // [T] reduce_tiles schedule, heaviest tiles first: {tile, pieces, first index entry, 0}
     uint32_t *cta_chunks;    // [bin CTAs] chunks each bin CTA used of its region
     uint2 *chunk_meta;       // [P] {tile, count}
     uint32_t *chunk_index;   // [P] per-tile chunk lists: id | (count-1) << 23
@@ -506,16 +506,15 @@ __device__ __forceinline__ void scan_tiles_body(const Ws &ws, const KParams &kp,
 #pragma unroll
     for (int q = 0; q < LPT; ++q) s_lvl[tid * LPT + q] += lbase;
     __syncthreads();
+    // counting sort by weight level: tile_sched lists the heaviest tiles first so that the persistent reduce CTAs
+    // finish together (longest-processing-time-first); an entry is everything reduce_tiles needs to start on the tile
     for (int t = lo; t < hi; ++t) {
+        const uint32_t c = __ldcg(&ws.tile_nchunks[t]);
         ws.tile_first[t] = run;
-        run += __ldcg(&ws.tile_nchunks[t]);
-    }
-    // counting sort by weight level: tile_order lists the heaviest tiles first so that the persistent
-    // reduce CTAs finish together (longest-processing-time-first)
-    for (int t = lo; t < hi; ++t) {
-        const uint32_t lvl = 1023u - min(__ldcg(&ws.tile_nchunks[t]), 1023u);
+        const uint32_t lvl = 1023u - min(c, 1023u);
         const uint32_t pos = atomicAdd(&s_lvl[lvl], 0xFFFFFFFFu) - 1u;      // fill each level's slot range from its end
-        ws.tile_order[pos] = (uint32_t)t;
+        ws.tile_sched[pos] = make_uint4((uint32_t)t, c, run, 0u);
+        run += c;
     }
 }
 
@@ -534,15 +533,19 @@ __device__ __forceinline__ uint32_t atoms_cas_u32(uint32_t a, uint32_t cmp, uint
     asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(v) : "memory");
     return old;
 }
-// slot of `tile` in the table at sm_key (claims an empty slot on first sight); CT_EMPTY if the table is full
-__device__ __forceinline__ uint32_t ct_find(uint32_t sm_key, uint32_t tile) {
-    uint32_t s = (tile * 2654435761u) >> (32 - 10);
+// home slot of a tile id
+__device__ __forceinline__ uint32_t ct_hash(uint32_t tile) {
     static_assert(CT_SLOTS == 1 << 10, "hash width");
+    return (tile * 2654435761u) >> (32 - 10);
+}
+// slot of `tile` in the table at sm_key, probing from slot s whose key was just read as k (claims an empty slot on
+// first sight); CT_EMPTY if the table is full
+__device__ __noinline__ uint32_t ct_find_slow(uint32_t sm_key, uint32_t tile, uint32_t s, uint32_t k) {
     for (int probe = 0; probe < CT_SLOTS; ++probe) {
-        uint32_t k = lds_u32(sm_key + 4u * s);
         if (k == CT_EMPTY) k = atoms_cas_u32(sm_key + 4u * s, CT_EMPTY, tile);
         if (k == tile || k == CT_EMPTY) return s;            // found, or claimed just now
         s = (s + 1u) & (CT_SLOTS - 1);
+        k = lds_u32(sm_key + 4u * s);
     }
     return CT_EMPTY;
 }
@@ -729,13 +732,20 @@ __device__ __forceinline__ void bin_points_body(const KParams &kp, const float4 
         uint32_t sa[BIN_PPT];                                    // shared address of the point's ring slot
         uint32_t en[BIN_PPT];                                    // entry of the append state: the tile id, or its table slot
 #pragma unroll
-        for (int j = 0; j < BIN_PPT; ++j) {
-            en[j] = tl[j];
-            if (CT && tl[j] != INVALID_U32) {
-                en[j] = ct_find(sm_key, tl[j]);
-                if (en[j] == CT_EMPTY) {                         // more tiles than the table holds: the gated kernels redo the call
-                    atomicExch(&ws.stats->ct_overflow, 1u);
-                    tl[j] = INVALID_U32;
+        for (int j = 0; j < BIN_PPT; ++j) en[j] = CT ? ct_hash(tl[j]) : tl[j];
+        if (CT) {
+            // all home-slot keys first (independent loads); a tile nearly always sits in its home slot
+            uint32_t k[BIN_PPT];
+#pragma unroll
+            for (int j = 0; j < BIN_PPT; ++j) k[j] = lds_u32(sm_key + 4u * en[j]);
+#pragma unroll
+            for (int j = 0; j < BIN_PPT; ++j) {
+                if (tl[j] != INVALID_U32 && k[j] != tl[j]) {
+                    en[j] = ct_find_slow(sm_key, tl[j], en[j], k[j]);
+                    if (en[j] == CT_EMPTY) {                     // more tiles than the table holds: the gated kernels redo the call
+                        atomicExch(&ws.stats->ct_overflow, 1u);
+                        tl[j] = INVALID_U32;
+                    }
                 }
             }
         }
@@ -1062,7 +1072,8 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     if (gated_off(ws)) return;
     constexpr int NW = popc6(MASK);
     extern __shared__ __align__(16) uint32_t acc[];      // [NW][cells]; plane 0/1 reused as packed/count16
-    __shared__ int s_tile;
+    __shared__ uint4 s_desc[2];                          // schedule entries of the current and the next tile (by parity)
+    __shared__ uint32_t s_claim, s_claim_end;            // schedule positions this CTA has claimed and not yet fetched
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TH = 1 << kp.tile_h_log2;
     const int cells = TH << TILE_W_LOG2;
@@ -1072,18 +1083,22 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     uint32_t *a_maxi = acc + plane_of(MASK, M_MAXI) * cells;
     uint32_t *a_minz = acc + plane_of(MASK, M_MINZ) * cells;   // holds max(256 - zq): 0 = empty
     uint32_t *a_maxz = acc + plane_of(MASK, M_MAXZ) * cells;
-    __shared__ uint32_t s_in, s_cnt;                     // records streamed into / counted in the current tile
+    __shared__ uint32_t s_in[2], s_cnt[2];               // records streamed into / counted in the current tile (by parity)
     __shared__ float s_div255[256];                      // u8 / 255 (one IEEE division each): the proj values
     if (out.proj) for (int i = tid; i < 256; i += RED_THREADS) s_div255[i] = __fdiv_rn((float)i, 255.0f);
     // Every candidate channel value is one byte.  They sit in two registers, A = [max_z | min_z | mean_i | max_i] and
     // B = [0 | 0 | density | mean_z], and ONE byte permute with this selector assembles a pixel's output word
     // (nibble c = which of the eight bytes channel c takes; byte 6 is zero for the channels past nch).
-    uint32_t ch_sel = 0;
-    for (int c = 0; c < 4; ++c) {
-        const int ch = c < kp.nch ? kp.ch[c] : -1;
-        const uint32_t idx = ch == LM_CH_MAX_I ? 0u : ch == LM_CH_MEAN_I ? 1u : ch == LM_CH_MIN_Z ? 2u : ch == LM_CH_MAX_Z ? 3u
-                           : ch == LM_CH_MEAN_Z ? 4u : ch == LM_CH_DENSITY ? 5u : 6u;
-        ch_sel |= idx << (4 * c);
+    __shared__ uint32_t s_sel;                           // (in shared memory: not a register held across the streaming loop)
+    if (tid == 0) {
+        uint32_t sel = 0;
+        for (int c = 0; c < 4; ++c) {
+            const int ch = c < kp.nch ? kp.ch[c] : -1;
+            const uint32_t idx = ch == LM_CH_MAX_I ? 0u : ch == LM_CH_MEAN_I ? 1u : ch == LM_CH_MIN_Z ? 2u : ch == LM_CH_MAX_Z ? 3u
+                               : ch == LM_CH_MEAN_Z ? 4u : ch == LM_CH_DENSITY ? 5u : 6u;
+            sel |= idx << (4 * c);
+        }
+        s_sel = sel;
     }
     auto zero_tile = [&]() {
         uint4 *a4 = reinterpret_cast<uint4 *>(acc);
@@ -1092,21 +1107,45 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
     };
     zero_tile();            // the finish pass of every tile leaves the planes zeroed for the next one
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) { s_tile = (int)atomicAdd(&ws.ctl->tile_counter, 1u); s_in = 0; s_cnt = 0; }
-        __syncthreads();
-        if (s_tile >= kp.T) break;
-        const int t = (int)ws.tile_order[s_tile];               // heaviest tiles first
-        const int trow = t / kp.tiles_x, tcol = t - trow * kp.tiles_x;
-        const int grow0 = trow << kp.tile_h_log2, gcol0 = tcol << TILE_W_LOG2;
-        const int nrows = min(TH, kp.H - grow0), ncols = min(TILE_W, kp.W - gcol0);
-        const uint32_t nchunks = ws.tile_nchunks[t];
-        const uint32_t *my_index = ws.chunk_index + ws.tile_first[t];
-        const int orow0 = kp.orow + grow0;                       // first row of this tile in the output buffers
-        // raw planes: everywhere (band <= 0) or only for tiles touching the halo bands.  In band mode
-        // only the planes the requested channels need are accumulated; the others are written as empty.
-        const bool want_raw = out.acc != nullptr && (kp.band <= 0 || tile_in_band(kp, t));
+    // A tile's schedule entry is fetched while the CTA streams the tile before it (thread 0, asynchronously), and the
+    // first pieces of the next tile are pulled into L2 before the current one is finished: a
+    // fine raster has ~1 point per cell, a tile's stream is ONE piece per warp, and the chain claim -> entry -> index
+    // -> records would otherwise be paid in full, serially, for each of a CTA's ~80 tiles.
+    constexpr uint32_t NO_TILE = 0xFFFFFFFFu;
+    // schedule entry i -> s_desc[slot], asynchronously (LDGSTS: no register waits for it); complete after sched_wait()
+    auto fetch_sched = [&](uint32_t i, int slot) {
+        if (i < (uint32_t)kp.T)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s_desc[slot])), "l"(ws.tile_sched + i) : "memory");
+        else
+            s_desc[slot] = make_uint4(NO_TILE, 0u, 0u, 0u);
+    };
+    auto sched_wait = [&]() { asm volatile("cp.async.wait_all;" ::: "memory"); };
+    // schedule positions are claimed in runs of `run` (one atomic round trip, paid by warp 0 only, per run): 1 unless a
+    // CTA has many tiles to go through (>= 32), up to 8
+    const uint32_t run = min(8u, max(1u, (uint32_t)kp.T / (gridDim.x * 16u)));
+    if (tid == 0) {
+        const uint32_t i0 = atomicAdd(&ws.ctl->tile_counter, run);
+        fetch_sched(i0, 0);
+        s_claim = i0 + 1u;
+        s_claim_end = i0 + run;
+        s_in[0] = s_in[1] = s_cnt[0] = s_cnt[1] = 0u;
+        sched_wait();
+    }
+    for (int it = 0;; ++it) {
+        const int par = it & 1;
+        __syncthreads();                   // s_desc[par] is set; the previous tile's finish pass has zeroed every plane
+        if (s_desc[par].x == NO_TILE) break;
+        if (tid == 0) {                    // the next tile's entry: in flight while this tile is streamed
+            uint32_t c = s_claim;
+            if (c == s_claim_end) {
+                c = atomicAdd(&ws.ctl->tile_counter, run);
+                s_claim_end = c + run;
+            }
+            s_claim = c + 1u;
+            fetch_sched(c, par ^ 1);
+        }
+        const uint32_t nchunks = s_desc[par].y;
+        const uint32_t *my_index = ws.chunk_index + s_desc[par].z;
 
         // ---- stream the tile's chunks with integer atomics in shared memory; count+sum packed in one
         //      word when possible, redone unpacked if a cell's count field overflowed
@@ -1116,12 +1155,32 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         const bool packed_ok = CAN_PACK && round == 0;
         if (packed_ok) {
             const uint32_t streamed = stream_tile<MASK, CAN_PACK>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
-            if (lane == 0 && streamed) atomicAdd(&s_in, streamed);
+            if (lane == 0 && streamed) atomicAdd(&s_in[par], streamed);
         } else {
             stream_tile<MASK, false>(ws, my_index, nchunks, warp, lane, a_cnt, a_sumi, a_sumz, a_maxi, a_minz, a_maxz);
         }
+        if (round == 0 && tid == 0) sched_wait();
         __syncthreads();
+        if (round == 0) {
+            if (tid == 0) s_in[par ^ 1] = s_cnt[par ^ 1] = 0u;     // (everybody is past the previous tile's comparison)
+            const uint4 dn = s_desc[par ^ 1];                    // the next tile: its first pieces into L2, one per warp
+            if (lane == 0 && dn.x != NO_TILE && (uint32_t)warp < dn.y) {
+                const uint32_t e = __ldg(ws.chunk_index + dn.z + warp);
+                const uint32_t bytes = ((((e >> IDX_ID_BITS) + 1u) * 4u) + 15u) & ~15u;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ws.pool + (size_t)(e & ((1u << IDX_ID_BITS) - 1u)) * PIECE_RECS), "r"(bytes) : "memory");
+            }
+        }
         uint32_t counted = 0;                                    // packed round: sum of this thread's cell counts
+        // (the tile's geometry is derived here, behind the stream, so that no register carries it through the stream)
+        const int t = (int)s_desc[par].x;                        // heaviest tiles first
+        const int trow = t / kp.tiles_x, tcol = t - trow * kp.tiles_x;
+        const int grow0 = trow << kp.tile_h_log2, gcol0 = tcol << TILE_W_LOG2;
+        const int nrows = min(TH, kp.H - grow0), ncols = min(TILE_W, kp.W - gcol0);
+        const int orow0 = kp.orow + grow0;                       // first row of this tile in the output buffers
+        // raw planes: everywhere (band <= 0) or only for tiles touching the halo bands.  In band mode
+        // only the planes the requested channels need are accumulated; the others are written as empty.
+        const bool want_raw = out.acc != nullptr && (kp.band <= 0 || tile_in_band(kp, t));
+        const uint32_t ch_sel = s_sel;
 
         // ---- finish + write-out in one pass: every thread takes 4 neighbouring cells of a row (a warp
         //      covers a whole 128-cell tile row), derives the channels, assembles the output words in
@@ -1234,9 +1293,9 @@ __global__ void __launch_bounds__(RED_THREADS, RED_MIN_CTAS) reduce_tiles_kernel
         if (!packed_ok) break;
         // conservation check of the packed round (block-uniform outcome)
         for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
-        if (lane == 0 && counted) atomicAdd(&s_cnt, counted);
+        if (lane == 0 && counted) atomicAdd(&s_cnt[par], counted);
         __syncthreads();
-        if (s_cnt == s_in) break;
+        if (s_cnt[par] == s_in[par]) break;
         __syncthreads();                                         // every thread has compared before the next round
         }
     }
@@ -1507,7 +1566,7 @@ int make_layout(const lm_bev_params *p, long long n, int algo, int T, Layout *L,
     L->off_nchunks = o; o = align_up(o + (size_t)T * 4, 256);
     L->off_first = o;   o = align_up(o + (size_t)T * 4, 256);
     L->off_cursor = o;  o = align_up(o + (size_t)T * 4, 256);
-    L->off_order = o;   o = align_up(o + (size_t)T * 4, 256);
+    L->off_order = o;   o = align_up(o + (size_t)T * sizeof(uint4), 256);
     const long long gb = ct ? bin_ctas_bound_smem(bin_ct_smem_bytes()) : bin_ctas_bound(T);
     const int T_open = ct && T > CT_SLOTS ? CT_SLOTS : T;      // open chunks a bin CTA can hold
     L->off_cta = o;     o = align_up(o + (size_t)gb * 4, 256);
@@ -1663,7 +1722,7 @@ Ws bind_ws(unsigned char *w, const Layout &L) {
     ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
     ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
     ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
-    ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
+    ws.tile_sched = reinterpret_cast<uint4 *>(w + L.off_order);
     ws.cta_chunks = reinterpret_cast<uint32_t *>(w + L.off_cta);
     ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
     ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
@@ -2114,19 +2173,7 @@ int lm_bev_rasterize_batch(const lm_bev_params *p, int32_t n_samples, const lm_b
         rc = make_layout(&ps, total, LM_ALGO_BINNED, kp.T, &L);      // sized like lm_bev_workspace_bytes_batch
         if (rc) return rc;
         if (workspace_bytes < L.total) return fail(LM_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, L.total);
-        Ws ws;
-        ws.stats = reinterpret_cast<lm_bev_stats *>(w);
-        ws.ctl = reinterpret_cast<Ctl *>(w + L.off_ctl);
-        ws.tile_nchunks = reinterpret_cast<uint32_t *>(w + L.off_nchunks);
-        ws.tile_first = reinterpret_cast<uint32_t *>(w + L.off_first);
-        ws.tile_cursor = reinterpret_cast<uint32_t *>(w + L.off_cursor);
-        ws.tile_order = reinterpret_cast<uint32_t *>(w + L.off_order);
-        ws.cta_chunks = reinterpret_cast<uint32_t *>(w + L.off_cta);
-        ws.chunk_meta = reinterpret_cast<uint2 *>(w + L.off_meta);
-        ws.chunk_index = reinterpret_cast<uint32_t *>(w + L.off_index);
-        ws.pool = reinterpret_cast<uint32_t *>(w + L.off_pool);
-        ws.acc = nullptr;
-        ws.pool_chunks = L.pool_chunks;
+        Ws ws = bind_ws(w, L);
         const size_t skip = s0 == 0 ? 0 : L.off_ctl;             // stats accumulate over the launch sets
         cudaError_t e = cudaMemsetAsync(w + skip, 0, L.zero_bytes - skip, st);
         if (e != cudaSuccess) return cuda_fail(e, "memset");
