@@ -158,3 +158,22 @@ def test_plan_api_without_a_gpu(native_lib):
             need = C.c_size_t(0)
             assert native_lib.lm_bev_workspace_bytes(C.byref(pp), 5_000_000, _cabi.ALGO_BINNED, C.byref(oo), C.byref(need)) == 0
             assert need.value <= bound.value, (h, w, outs)
+    # compact-table pass (tuning bin_compact_table): automatic on a raster whose tile count leaves direct indexing fewer
+    # than three bin CTAs per SM -- the plan then sizes for both layouts; -1 sizes for the direct-indexed kernels alone,
+    # +1 asks for the pass on a raster that would not take it (no more open chunks per CTA than the raster has tiles)
+    fine, coarse = _cabi.make_params(BevSpec(28800, 3456, count16=True)), _cabi.make_params(BevSpec(2304, 1152))
+    oo = _cabi.LmBevOutputs()
+    oo.image_dev = 1
+    sizes = {}
+    for name, pp in (("fine", fine), ("coarse", coarse)):
+        for mode in (0, 1, -1):
+            tt = _cabi.LmBevTuning()
+            tt.bin_compact_table = mode
+            pl = C.c_void_p()
+            assert native_lib.lm_bev_plan_create(C.byref(pp), 5_000_000, _cabi.ALGO_BINNED, C.byref(oo), C.byref(tt), C.byref(pl)) == 0
+            nb = C.c_size_t(0)
+            assert native_lib.lm_bev_plan_workspace_bytes(pl, C.byref(nb)) == 0
+            sizes[name, mode] = nb.value
+            native_lib.lm_bev_plan_destroy(pl)
+    assert sizes["fine", 0] == sizes["fine", 1] >= sizes["fine", -1]
+    assert sizes["coarse", 0] == sizes["coarse", -1] <= sizes["coarse", 1]
