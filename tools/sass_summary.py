@@ -19,7 +19,9 @@ for block in sass.split("Function : ")[1:]:
         name = subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip() or name
     except FileNotFoundError:
         pass
-    name = name.replace("<unnamed>::", "").split("(")[0].replace("void ", "")
+    name = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").replace("void ", "")
+    m = re.match(r"^(\w+(?:<[^>]*>)?)", name)                   # kernel name + template arguments, no parameter list
+    name = m.group(1) if m else name
     ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", block)
     special, mem = collections.Counter(), collections.Counter()
     for op in ops:
