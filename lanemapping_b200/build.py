@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, os.path.basename(os.environ.get("LM_BEV_LIB", "") or "liblm_bev.so"))
 SOURCES = [os.path.join(CSRC, "lm_bev.cu"), os.path.join(CSRC, "lm_post.cu")]
 HEADERS = [os.path.join(ROOT, "include", h) for h in ("lm_bev.h", "lm_las.h", "lm_post.h")] + \
-          [os.path.join(CSRC, h) for h in ("lm_dev.cuh", "lm_host.h")]
+          [os.path.join(CSRC, h) for h in ("lm_dev.cuh", "lm_sweep.cuh", "lm_host.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
