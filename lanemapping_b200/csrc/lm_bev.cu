@@ -485,13 +485,15 @@ __device__ __forceinline__ void scan_tiles_body(const Ws &ws, const KParams &kp,
     }
     for (int i = tid; i < 1024; i += NT) s_lvl[i] = 0;
     __syncthreads();
-    const int per = (T + NT - 1) / NT;
-    const int lo = tid * per, hi = min(T, lo + per);
+    // Thread `tid` owns tiles tid, tid + NT, ... (coalesced table accesses; a raster of 24 300 tiles spent 48 us here
+    // with one contiguous range per thread).  A tile's pieces only have to be contiguous in the index, in whatever
+    // order the tiles follow each other: thread by thread, each thread's tiles in ascending order.
     if (s_flag[0]) {   // pool exhausted: publish an empty raster instead of reading half-built lists
-        for (int t = lo; t < hi; ++t) ws.tile_nchunks[t] = 0;
+        for (int t = tid; t < T; t += NT) ws.tile_nchunks[t] = 0;
     }
     uint32_t sum = 0;
-    for (int t = lo; t < hi; ++t) {
+#pragma unroll 4
+    for (int t = tid; t < T; t += NT) {
         const uint32_t c = __ldcg(&ws.tile_nchunks[t]);      // other CTAs' atomics: read at the L2
         sum += c;
         atomicAdd(&s_lvl[1023u - min(c, 1023u)], 1u);      // level 0 = heaviest
@@ -508,7 +510,8 @@ __device__ __forceinline__ void scan_tiles_body(const Ws &ws, const KParams &kp,
     __syncthreads();
     // counting sort by weight level: tile_sched lists the heaviest tiles first so that the persistent reduce CTAs
     // finish together (longest-processing-time-first); an entry is everything reduce_tiles needs to start on the tile
-    for (int t = lo; t < hi; ++t) {
+#pragma unroll 4
+    for (int t = tid; t < T; t += NT) {
         const uint32_t c = __ldcg(&ws.tile_nchunks[t]);
         ws.tile_first[t] = run;
         const uint32_t lvl = 1023u - min(c, 1023u);
