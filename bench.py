@@ -123,17 +123,19 @@ def numpy_single_thread(cloud, spec, n=5_000_000):
 
 
 def png_encode_ms(spec):
-    """ms to PNG-encode one 1152^2 crop the way the offline converter does (cv2, compression 1)."""
+    """ms to PNG-encode one 1152^2 crop the way the offline converter does (cv2, zlib level 1 + RLE strategy,
+    lanemapping_b200/convert_data.py::png_params), on one host thread."""
     import cv2
+    from lanemapping_b200.convert_data import png_params
     from lanemapping_b200.synth import make_cloud
     from oracle import bev_oracle as O
     from dataclasses import replace
     sp = replace(spec, height=1152, width=1152, row0=0, col0=0)
     img = O.rasterize(make_cloud(2_000_000, sp, order="scan"), sp)["image"]
-    cv2.imencode(".png", img, [cv2.IMWRITE_PNG_COMPRESSION, 1])
+    cv2.imencode(".png", img, png_params())
     t0 = time.perf_counter()
     for _ in range(3):
-        cv2.imencode(".png", img, [cv2.IMWRITE_PNG_COMPRESSION, 1])
+        cv2.imencode(".png", img, png_params())
     return (time.perf_counter() - t0) / 3 * 1e3
 
 

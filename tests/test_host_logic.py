@@ -69,3 +69,30 @@ def test_seq_ids_are_unique_per_run_and_read_offset_comes_from_the_data(tmp_path
     open(path, "wb").write(bytes(blank))
     raw2, hdr2 = las.read_point_block(path)
     assert not hdr2.bounds_ok() and las.world_min(raw2, hdr2) == (10.5, 19.0, 2.5)
+
+
+def test_png_writer_is_lossless_in_pil_channel_order_and_pool_propagates_errors(tmp_path):
+    """The converter's PNG writer (zlib level 1 + RLE strategy, crops of one file encoded by a shared thread pool):
+    what PIL reads back -- the loader's view, reference baseline/datasets/laserlane_proposals.py:88-89 -- is the
+    raster byte for byte, channel c of the raster in channel c of the PIL image; a failing write raises in the caller."""
+    from PIL import Image
+    from lanemapping_b200 import convert_data as CD
+    rng = np.random.default_rng(3)
+    imgs = {}
+    for c in (3, 4):
+        img = np.zeros((96, 160, c), dtype=np.uint8)
+        occ = rng.random((96, 160)) < 0.7
+        img[occ] = rng.integers(0, 256, (int(occ.sum()), c), dtype=np.uint8)
+        imgs[c] = img
+    pool = CD._encode_pool()
+    assert pool is CD._encode_pool()                       # one pool per process
+    futs = [pool.submit(CD._write_png, str(tmp_path / f"c{c}_{i}.png"), imgs[c]) for c in (3, 4) for i in range(4)]
+    for f in futs:
+        f.result()
+    for c in (3, 4):
+        for i in range(4):
+            back = np.asarray(Image.open(tmp_path / f"c{c}_{i}.png"))
+            assert back.shape == imgs[c].shape and np.array_equal(back, imgs[c])
+    bad = pool.submit(CD._write_png, str(tmp_path / "no_such_dir" / "x.png"), imgs[3])
+    with pytest.raises(Exception):
+        bad.result()
