@@ -139,6 +139,15 @@ def _encode_pool():
         return _encoders
 
 
+def shutdown_encoders() -> None:
+    """Join the encoder threads (a later ``_encode_pool()`` starts new ones): for callers that fork afterwards."""
+    global _encoders
+    with _lock:
+        pool, _encoders = _encoders, None
+    if pool is not None:
+        pool.shutdown(wait=True)
+
+
 # ---- process-wide state of a conversion run -------------------------------------------------------------
 _lock = threading.Lock()
 _claimed: Dict[Tuple[str, str], str] = {}       # (output dir, stem) -> source file that wrote it in this process

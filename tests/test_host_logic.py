@@ -96,3 +96,5 @@ def test_png_writer_is_lossless_in_pil_channel_order_and_pool_propagates_errors(
     bad = pool.submit(CD._write_png, str(tmp_path / "no_such_dir" / "x.png"), imgs[3])
     with pytest.raises(Exception):
         bad.result()
+    CD.shutdown_encoders()                                 # (later tests fork: leave no threads behind)
+    assert CD._encoders is None
